@@ -1,0 +1,74 @@
+/* sdqlpy-b200 C ABI -- the boundary every generated query module (<script>_compiled.so) exports.
+ *
+ * What it replaces in the reference (edin-dal/sdqlpy):
+ *   - the generated CPython method  <fn>_compiled(db)        sdql_compiler.py:601-672, 749-777
+ *     (numpy column pointers in: PyArray_DATA casts           sdql_compiler.py:644-668)
+ *   - the result boxing into a FastDict / PyFloat / PyLong    sdql_ir_cpp_generator_par.py:866-877
+ * The reference has no plain C ABI (its C-API function *is* the ABI); this header is
+ * the interface a maintainer binds instead (ctypes stub in INTEGRATION.md; sdqlpy_b200/runtime.py is that stub).
+ *
+ * Conventions: plain pointers and sizes only, no exceptions cross the boundary, every function returns 0 on
+ * success and a negative SDQLB200_E_* code otherwise (text via sdqlb200_last_error()).
+ */
+#ifndef SDQLB200_H
+#define SDQLB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { SDQLB200_I32 = 0, SDQLB200_F64 = 1, SDQLB200_CODE = 2, SDQLB200_BYTES = 3 };
+enum { SDQLB200_OK = 0, SDQLB200_E_WORKSPACE = -1, SDQLB200_E_CUDA = -2, SDQLB200_E_ARG = -3, SDQLB200_E_NOQUERY = -4 };
+enum { SDQLB200_F_NOFETCH = 1 };
+
+/* one device-resident column (replaces the borrowed numpy buffer of sdql_compiler.py:653-668) */
+typedef struct {
+    const void* data; /* DEVICE pointer, 16-byte aligned                                         */
+    int64_t rows;
+    int64_t min, max; /* value range of int/date columns; [0, dictionary size - 1] for codes    */
+    int32_t width;    /* element bytes: I32 4, F64 8, CODE 1 or 4, BYTES = fixed string width   */
+    int32_t kind;     /* SDQLB200_I32 | F64 | CODE | BYTES                                       */
+} sdqlb200_col;
+
+/* result rows in SoA form; every field is one 8-byte slot per row (int64 / fp64 bits / string reference) */
+typedef struct {
+    int64_t count;
+    int32_t nfields;
+    int32_t reserved;
+    int64_t* cols[32]; /* HOST buffers owned by the library until sdqlb200_result_free */
+} sdqlb200_result;
+
+typedef struct {
+    const sdqlb200_col* cols; /* in the order of the query manifest's "inputs"                 */
+    int32_t ncols;
+    int32_t nargs;
+    const int64_t* nrows;     /* rows of each relation argument, in query-argument order        */
+    const int64_t* consts;    /* resolved constants, in the order of the manifest's "consts"   */
+    int32_t nconsts;
+    int32_t flags;            /* SDQLB200_F_*                                                   */
+    void* workspace;          /* DEVICE scratch (tables, partials, result buffers)              */
+    uint64_t workspace_bytes;
+    uint64_t workspace_needed; /* out: set when SDQLB200_E_WORKSPACE is returned                */
+    void* stream;             /* cudaStream_t                                                   */
+    float device_ms;          /* out: CUDA-event time of all kernels + memsets of the query     */
+    int32_t launches;         /* out: kernels launched                                          */
+    int32_t tier;             /* out: aggregation tier of the last group-by kernel (0/1/2)      */
+    int32_t reserved;
+    sdqlb200_result result;   /* out                                                            */
+} sdqlb200_args;
+
+int sdqlb200_num_queries(void);
+const char* sdqlb200_query_name(int i);
+/* JSON: per query its arguments, required device inputs (arg, column, representation), constants to resolve,
+ * result schema and algorithmic bytes per scanned row */
+const char* sdqlb200_manifest(void);
+/* run one query (replaces <fn>_compiled(db)).  Call with workspace == NULL to obtain workspace_needed. */
+int sdqlb200_run(const char* query, sdqlb200_args* args);
+void sdqlb200_result_free(sdqlb200_result* r);
+const char* sdqlb200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

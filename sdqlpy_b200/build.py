@@ -1,0 +1,114 @@
+"""Compile driver: query script -> IR -> CUDA text -> nvcc (sm_100a) -> <script>_compiled.so.
+
+Replaces the reference's compile launcher + build script (compiler.sh:9-14, the generated fast_dict_setup.py of
+fast_dict_generator.py:125-171: g++ -O3 -std=c++17 -ltbb into site-packages).  The generated source is kept next
+to the shared object so kernels can be inspected / profiled with -lineinfo.
+"""
+import ast
+import hashlib
+import os
+import subprocess
+import sys
+
+from . import codegen, frontend
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+INC = os.path.join(ROOT, "include")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--use_fast_math=false",
+              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+
+
+def extract_schemas(tree):
+    """module-level ``name = {record({...}): bool}`` -> {name: [(col, kind)]} (kinds as in tpch.gen.SCHEMAS)."""
+    out = {}
+    for st in tree.body:
+        if not (isinstance(st, ast.Assign) and len(st.targets) == 1 and isinstance(st.targets[0], ast.Name)):
+            continue
+        v = st.value
+        if not (isinstance(v, ast.Dict) and len(v.keys) == 1 and isinstance(v.keys[0], ast.Call)
+                and getattr(v.keys[0].func, "id", None) == "record" and v.keys[0].args
+                and isinstance(v.keys[0].args[0], ast.Dict)):
+            continue
+        cols = []
+        d = v.keys[0].args[0]
+        for k, t in zip(d.keys, d.values):
+            if isinstance(t, ast.Call) and getattr(t.func, "id", None) == "string":
+                cols.append((k.value, ("str", t.args[0].value if t.args else 25)))
+            elif isinstance(t, ast.Name) and t.id in ("int", "float", "date", "bool"):
+                cols.append((k.value, t.id))
+            else:
+                raise codegen.CodegenError("unsupported column type for %s" % k.value)
+        out[st.targets[0].id] = cols
+    return out
+
+
+def compile_source(source, src_name="<string>", only=None):
+    """-> (CUDA text, [codegen.Query])"""
+    tree = ast.parse(source)
+    schemas = extract_schemas(tree)
+    funcs, consts = frontend.parse_module(source)
+    queries = []
+    for name, (fn, in_type) in funcs.items():
+        if only and name not in only:
+            continue
+        root, args = frontend.function_to_ir(fn, consts)
+        qs = {}
+        if isinstance(in_type, ast.Dict):
+            for k, v in zip(in_type.keys, in_type.values):
+                if not isinstance(v, ast.Name) or v.id not in schemas:
+                    raise codegen.CodegenError("%s: unknown schema for argument %s" % (name, k.value))
+                qs[k.value] = schemas[v.id]
+        for a in args:
+            if a not in qs:
+                raise codegen.CodegenError("%s: argument '%s' has no schema in @sdql_compile" % (name, a))
+        q = codegen.Query(name, args, qs)
+        try:
+            q.compile(root)
+        except codegen.CodegenError as e:
+            raise codegen.CodegenError("%s: %s" % (name, e)) from e
+        queries.append(q)
+    return codegen.render_module(queries, src_name), queries
+
+
+def out_paths(script_path):
+    script_path = os.path.abspath(script_path)
+    stem = os.path.splitext(os.path.basename(script_path))[0]
+    d = os.path.join(os.path.dirname(script_path), "sdqlb200_generated")
+    return os.path.join(d, stem + "_compiled.cu"), os.path.join(d, stem + "_compiled.so")
+
+
+def nvcc(cu, so, verbose=False):
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-I", CSRC, "-I", INC, cu, "-o", so]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout[-4000:] + r.stderr[-8000:])
+    log = r.stdout + r.stderr
+    open(so + ".ptxas.log", "w").write(log)
+    if verbose:
+        print(log)
+    return so
+
+
+def compile_file(script_path, force=False, verbose=False):
+    """generate + build the module of one query script; returns the .so path."""
+    cu, so = out_paths(script_path)
+    os.makedirs(os.path.dirname(cu), exist_ok=True)
+    source = open(script_path).read()
+    text, _ = compile_source(source, os.path.relpath(script_path, ROOT) if script_path.startswith(ROOT) else script_path)
+    digest = hashlib.sha256(text.encode()).hexdigest()
+    stamp = so + ".sha256"
+    deps = [os.path.join(CSRC, f) for f in ("sdqlb200_rt.cuh", "sdqlb200_host.h")] + [os.path.join(INC, "sdqlb200.h")]
+    fresh = (os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == digest
+             and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps))
+    if fresh and not force:
+        return so
+    open(cu, "w").write(text)
+    nvcc(cu, so, verbose)
+    open(stamp, "w").write(digest)
+    return so
+
+
+if __name__ == "__main__":
+    print(compile_file(sys.argv[1], force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,1616 @@
+"""SDQL IR -> sm_100a CUDA.   Replaces the reference's C++/TBB generator
+(/root/reference/src/sdqlpy/lib/sdql_ir_cpp_generator_par.py:12-637, ``GenerateCPPCode``).
+
+The reference lowers every ``SumExpr`` over a relation to one of five TBB loop templates (gen:188-568) that fill
+thread-local phmap tables and merge them serially.  Here every sum becomes ONE fused CUDA kernel
+(scan + predicates + probes + aggregation inlined, the operator fusion SDQL exists for), assembled from the
+hand-written device runtime in csrc/sdqlb200_rt.cuh:
+
+  reference template (gen: lines)                     this generator
+  ------------------------------------------------    -------------------------------------------------------------
+  dense-array sum              gen:191-224, 472-495   BuildSink/GroupSink on a direct-indexed Tbl (domain from column
+                                                      statistics at run time; the literal N of dense(N, ..) is ignored)
+  scalar / record reduction    gen:258-291            ReduceSink: register accumulators -> block tree -> last-block tree
+  dictionary build ("unique")  gen:293-369            BuildSink: key -> representative row id (CAS claim); payload
+                                                      fields are re-evaluated from the representative row on use
+  dictionary aggregation       gen:402-440            GroupSink: 3 tiers picked at run time -- thread-private shared
+                                                      memory, CTA-shared shared memory atomics, global atomics
+  local / finalisation sums    gen:520-568            the same kernels over table slots; result sets -> ResultSink
+  probes  .contains()/.at()    gen:85-96              tbl_find on packed keys (mixed radix from column statistics)
+
+The lowering is a symbolic evaluation of the IR: expressions evaluate to ``S*`` values carrying C++ text plus
+provenance, which is what allows group keys to be minimised by functional dependency (e.g. Q3's
+<l_orderkey, o_orderdate, o_shippriority> is keyed by l_orderkey alone) and wide payloads (strings) to stay
+on the host until the result is boxed (late materialisation by row id).
+"""
+import json
+from collections import OrderedDict
+
+from . import ir
+from .ir import CompareSymbol as CS
+from .ir import ExtFuncSymbol as XF
+
+
+class CodegenError(Exception):
+    pass
+
+
+# =============================================================================================
+# symbolic values
+# =============================================================================================
+E = frozenset()
+
+
+class SScalar:
+    def __init__(self, ctype, code, prov=E, det=E, stats=None):
+        self.ctype, self.code, self.prov, self.det, self.stats = ctype, code, prov, det, stats
+
+
+class SStr:
+    """kind: 'const' (value) | 'ref' (arg, col, row) | 'codeval' (arg, col, code) | 'pack' (n, code)"""
+
+    def __init__(self, kind, **kw):
+        self.kind = kind
+        self.prov, self.det = kw.pop("prov", E), kw.pop("det", E)
+        self.__dict__.update(kw)
+
+
+class SRec:
+    def __init__(self, fields):
+        self.fields = OrderedDict(fields)
+
+    def field(self, K, name):
+        if name not in self.fields:
+            raise CodegenError("record has no field '%s' (has %s)" % (name, list(self.fields)))
+        v = self.fields[name]
+        return v() if callable(v) else v
+
+    def items(self, K):
+        return [(n, self.field(K, n)) for n in self.fields]
+
+
+class SRow:
+    """record = row ``row`` of relation argument ``arg``."""
+
+    def __init__(self, q, arg, row, scan=False, prov=E, keycode=None, token=None):
+        self.q, self.arg, self.row, self.scan, self.prov, self.keycode, self.token = q, arg, row, scan, prov, keycode, token
+
+    def field(self, K, name):
+        return self.q.col_value(K, self, name)
+
+    def items(self, K):
+        return [(n, self.field(K, n)) for n, _ in self.q.schemas[self.arg]]
+
+
+class SPair:
+    def __init__(self, k, v):
+        self.k, self.v = k, v
+
+
+class SNone:
+    pass
+
+
+class STable:
+    def __init__(self, desc):
+        self.desc = desc
+
+
+class SDictLit:
+    def __init__(self, k, v):
+        self.k, self.v = k, v
+
+
+class SVecLit:
+    def __init__(self, elem):
+        self.elem = elem
+
+
+class SLookup:
+    def __init__(self, K, table, slot, token):
+        self.K, self.table, self.slot, self.token = K, table, slot, token
+        self.found = "(%s >= 0)" % slot
+        self._val = None
+
+    def value(self):
+        if self._val is None:
+            self._val = self.table.value_at(self.K, self.slot, self.token, safe=True)
+        return self._val
+
+
+TRUE = SScalar("bool", "true")
+CT = {"i64": "long long", "f64": "double", "bool": "bool"}
+
+
+def lit_f64(v):
+    r = repr(float(v))
+    if "e" not in r and "." not in r and "inf" not in r and "nan" not in r:
+        r += ".0"
+    return r
+
+
+def cstr(s):
+    return '"' + s.replace("\\", "\\\\").replace('"', '\\"') + '"'
+
+
+# =============================================================================================
+# tables
+# =============================================================================================
+class TableDesc:
+    """compile-time description of one device dictionary."""
+
+    def __init__(self, q, name, kind):
+        self.q, self.name, self.kind = q, name, kind  # kind: 'build' | 'agg'
+        self.parts = []         # by-value key parts: stats tuples
+        self.fields = []        # aggregate fields [(name or None, ctype)]
+        self.scalar_value = False
+        self.count_only = False
+        self.src = None         # ('rel', arg) | ('tbl', TableDesc)
+        self.key_fn = None      # (K, idx_code) -> key SValue   (rep-evaluation)
+        self.val_fn = None      # build: (K, idx_code) -> value SValue
+        self.inner = None       # nested dict value: (n_outer_parts, [inner stats], inner key template SValue)
+        self.distinct_of = None
+
+    # -- element access ---------------------------------------------------------------------
+    def src_elem(self, K, idx, prov=E):
+        """the (key, value) pair of this table's *source* at source index idx."""
+        if self.src[0] == "rel":
+            return SPair(SRow(self.q, self.src[1], idx, scan=False, prov=prov), TRUE)
+        t = self.src[1]
+        return SPair(t.key_at(K, idx, prov), t.value_at(K, idx, None, prov=prov))
+
+    def key_at(self, K, slot, prov=E):
+        """key of the entry in ``slot``: parts kept by value are decoded from the packed key, functionally
+        dependent parts are re-evaluated (lazily) at the slot's representative source index."""
+        rp_code = "sdqlrt::rep_of(c.%s, %s)" % (self.name, slot)
+
+        def rep_leaf(i):
+            def f():
+                rp = K.let("int", rp_code)
+                return flatten(K, self.key_fn(K, rp, prov))[i]
+            return f
+
+        shape = getattr(self, "key_shape", None)
+        if shape is None:  # never keyed through setup_key
+            rp = K.let("int", rp_code)
+            return self.key_fn(K, rp, prov)
+        kk = K.let("unsigned long long", "sdqlrt::tbl_key(c.%s, %s)" % (self.name, slot))
+        leaves = []
+        for i in range(self.full_arity):
+            if i in self.kept_pos:
+                j = self.kept_pos.index(i)
+                code = "sdqlrt::unpack_part(%s, c.%s_mn[%d], c.%s_rng[%d], c.%s_mul[%d])" % (kk, self.name, j, self.name, j, self.name, j)
+                leaves.append(decode_leaf(self.leaf_kinds[j], code, prov, self.parts[j]))
+            else:
+                leaves.append(rep_leaf(i))
+        if shape == "scalar":
+            v = leaves[0]
+            return v() if callable(v) else v
+        return SRec(list(zip(shape, leaves)))
+
+    def value_at(self, K, slot, token, safe=False, prov=E):
+        q = self.q
+        if token is not None:
+            prov = frozenset([token])
+        sl = "(%s < 0 ? 0 : %s)" % (slot, slot) if safe else slot
+        if self.kind == "agg":
+            vals = []
+            for j, (fname, ct) in enumerate(self.fields):
+                vals.append((fname, SScalar(ct, "sdqlrt::ld1(c.%s_a%d + %s)" % (self.name, j, sl), prov=prov)))
+            if self.inner is not None:
+                raise CodegenError("nested dictionary value used as a plain value")
+            if self.scalar_value or self.count_only:
+                return vals[0][1]
+            return SRec(vals)
+        rp = K.let("int", "sdqlrt::rep_of(c.%s, %s)" % (self.name, slot))
+        keycode = None
+        if token is not None:
+            kv = flatten(K, self.key_fn(K, rp, prov))
+            if len(kv) == 1 and hasattr(kv[0], "code"):
+                keycode = kv[0].code
+            elif len(kv) == 1 and kv[0].kind == "ref":
+                keycode = ("ref", kv[0].arg, kv[0].col, kv[0].row)
+        v = self.val_fn(K, rp, prov)
+        return mark(K, v, prov, keycode, token)
+
+
+def leaf_kind(x):
+    if isinstance(x, SScalar):
+        return (x.ctype,)
+    if x.kind in ("ref", "codeval"):
+        return ("codeval", x.arg, x.col)
+    if x.kind == "pack":
+        return ("pack", x.n)
+    raise CodegenError("unsupported key part")
+
+
+def decode_leaf(kind, code, prov, stats):
+    if kind[0] == "i64":
+        return SScalar("i64", code, prov, E, stats)
+    if kind[0] == "f64":
+        return SScalar("f64", "__longlong_as_double(%s)" % code, prov)
+    if kind[0] == "bool":
+        return SScalar("bool", "(%s != 0)" % code, prov)
+    if kind[0] == "codeval":
+        return SStr("codeval", arg=kind[1], col=kind[2], code=code, prov=prov)
+    return SStr("pack", n=kind[1], code=code, prov=prov)
+
+
+def mark(K, v, prov, keycode, token):
+    """stamp provenance on everything reachable from a lookup result (lazily for records)."""
+    if isinstance(v, SScalar):
+        det = frozenset([token]) if (token is not None and keycode is not None and v.code == keycode) else v.det
+        return SScalar(v.ctype, v.code, v.prov if v.prov else prov, det, v.stats)
+    if isinstance(v, SStr):
+        if v.kind == "const":
+            return v
+        d = dict(v.__dict__)
+        kind = d.pop("kind")
+        d["prov"] = v.prov if v.prov else prov
+        if token is not None and keycode == ("ref", d.get("arg"), d.get("col"), d.get("row")):
+            d["det"] = frozenset([token])
+        return SStr(kind, **d)
+    if isinstance(v, SRec):
+        def lazy(n):
+            return lambda: mark(K, v.field(K, n), prov, keycode, token)
+        return SRec([(n, lazy(n)) for n in v.fields])
+    if isinstance(v, SRow):
+        return SRow(v.q, v.arg, v.row, False, v.prov if v.prov else prov, keycode, token)
+    if isinstance(v, SLookup):
+        return mark(K, v.value(), prov, keycode, token)
+    return v
+
+
+def flatten(K, v):
+    """leaf values of a key in field order."""
+    if isinstance(v, (SScalar, SStr)):
+        return [v]
+    if isinstance(v, SLookup):
+        return flatten(K, v.value())
+    if isinstance(v, (SRec, SRow)):
+        out = []
+        for _, f in v.items(K):
+            out += flatten(K, f)
+        return out
+    raise CodegenError("cannot use %s as a dictionary key" % type(v).__name__)
+
+
+# =============================================================================================
+# kernels
+# =============================================================================================
+class Kernel:
+    def __init__(self, q, name, src):
+        self.q, self.name, self.src = q, name, src
+        self.body, self.pre, self.post = [], [], []
+        self.depth = 0
+        self.scan_cols = OrderedDict()   # (col, rep) -> (array name, input idx)
+        self.cse = [{}]
+        self.ntmp = 0
+        self.sink = None
+        self.tiered = False
+        self.smem_expr = "0"
+        self.tier_expr = "2"
+        self.scan_var = "i"
+
+    def emit(self, s):
+        self.body.append("    " * self.depth + s)
+
+    def tmp(self, p="t"):
+        self.ntmp += 1
+        return "%s%d" % (p, self.ntmp)
+
+    def let(self, ctype, expr):
+        key = (ctype, expr)
+        for scope in self.cse:
+            if key in scope:
+                return scope[key]
+        v = self.tmp()
+        self.emit("const %s %s = %s;" % (ctype, v, expr))
+        self.cse[-1][key] = v
+        return v
+
+    def open_if(self, cond):
+        self.emit("if (%s) {" % cond)
+        self.depth += 1
+        self.cse.append({})
+
+    def open_block(self, head):
+        self.emit(head + " {")
+        self.depth += 1
+        self.cse.append({})
+
+    def close(self):
+        self.cse.pop()
+        self.depth -= 1
+        self.emit("}")
+
+    def scan_col(self, col, rep):
+        k = (col, rep)
+        if k not in self.scan_cols:
+            idx = self.q.input(self.src[1], col, rep)
+            self.scan_cols[k] = ("r_%s%s" % (col, "_c" if rep == "code" else ""), idx)
+        return self.scan_cols[k][0] + "[u]"
+
+    # -- text -------------------------------------------------------------------------------
+    def render(self):
+        q = self.q
+        L = []
+        tmpl = "template <int TIER>\n" if self.tiered else ""
+        L.append("%s__global__ void __launch_bounds__(sdqlrt::kBlock) %s(const __grid_constant__ %s_ctx c) {" %
+                 (tmpl, self.name, q.name))
+        L += ["    " + s for s in self.pre]
+        if self.src[0] == "rel":
+            L.append("    const long long n = c.n_%s;" % self.src[1])
+            L.append("    const long long ngrp = (n + 3) >> 2;")
+            L.append("    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ngrp; "
+                     "g += (long long)gridDim.x * blockDim.x) {")
+            L.append("        const long long i0 = g << 2;")
+            for (col, rep), (arr, idx) in self.scan_cols.items():
+                ety = {"i32": "int", "f64": "double", "code": "int"}[rep]
+                L.append("        %s %s[4];" % (ety, arr))
+            L.append("        if (i0 + 4 <= n) {")
+            for (col, rep), (arr, idx) in self.scan_cols.items():
+                if rep == "code":
+                    L.append("            sdqlrt::ld4_code(c.in%d, i0, c.in%d_w, %s);" % (idx, idx, arr))
+                else:
+                    L.append("            sdqlrt::ld4(c.in%d + i0, %s);" % (idx, arr))
+            L.append("        } else {")
+            L.append("            for (int u = 0; u < 4; ++u) {")
+            L.append("                const long long ii = (i0 + u < n) ? i0 + u : n - 1;")
+            for (col, rep), (arr, idx) in self.scan_cols.items():
+                if rep == "code":
+                    L.append("                %s[u] = sdqlrt::ld1_code(c.in%d, ii, c.in%d_w);" % (arr, idx, idx))
+                else:
+                    L.append("                %s[u] = sdqlrt::ld1(c.in%d + ii);" % (arr, idx))
+            L.append("            }")
+            L.append("        }")
+            L.append("#pragma unroll")
+            L.append("        for (int u = 0; u < 4; ++u) {")
+            L.append("            const long long i = i0 + u;")
+            L.append("            if (i < n) {")
+            L += ["                " + s for s in self.body]
+            L.append("            }")
+            L.append("        }")
+            L.append("    }")
+        elif self.src[0] == "tbl":
+            t = self.src[1]
+            L.append("    const long long n = c.%s.cap;" % t.name)
+            L.append("    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; "
+                     "i += (long long)gridDim.x * blockDim.x) {")
+            L.append("        if (c.%s.rep[i] < 0) continue;" % t.name)
+            L += ["        " + s for s in self.body]
+            L.append("    }")
+        else:  # single-thread finalisation kernel
+            L.append("    if (blockIdx.x == 0 && threadIdx.x == 0) {")
+            L += ["        " + s for s in self.body]
+            L.append("    }")
+        L += ["    " + s for s in self.post]
+        L.append("}")
+        return "\n".join(L)
+
+
+# =============================================================================================
+# sinks
+# =============================================================================================
+def cast_to(v, ctype):
+    if v.ctype == ctype:
+        return v.code
+    return "(%s)(%s)" % (CT[ctype], v.code)
+
+
+class ReduceSink:
+    """A2: scalar / record reduction (gen:258-291)."""
+
+    def __init__(self, q, K, first):
+        self.q, self.K = q, K
+        self.fields = []     # (name, ctype, slot)
+        self.sub = {}        # field name -> GroupSink (dictionary-valued record field, Q11)
+        self.scalar = not isinstance(first, SRec)
+
+    def _acc(self, name, v):
+        for f in self.fields:
+            if f[0] == name:
+                return f
+        slot = self.q.new_scalar()
+        f = (name, v.ctype if v.ctype != "bool" else "i64", slot, "acc%d" % len(self.fields))
+        self.fields.append(f)
+        self.K.pre.append("%s %s = 0;" % (CT[f[1]], f[3]))
+        return f
+
+    def produce(self, v):
+        K = self.K
+        items = [(None, v)] if self.scalar else v.items(K)
+        for name, x in items:
+            if isinstance(x, SLookup):
+                x = x.value()
+            if isinstance(x, SDictLit):
+                if name not in self.sub:
+                    self.sub[name] = GroupSink(self.q, K, self.q.new_table("agg"), False)
+                self.sub[name].produce(x)
+                continue
+            if not isinstance(x, SScalar):
+                raise CodegenError("cannot reduce a %s" % type(x).__name__)
+            f = self._acc(name, x)
+            K.emit("%s += %s;" % (f[3], cast_to(x, f[1])))
+
+    def finish(self):
+        q, K = self.q, self.K
+        nf = len(self.fields)
+        if nf:
+            part = q.new_partials(nf)
+            cnt = q.new_counter()
+            K.post.append("{")
+            for j, f in enumerate(self.fields):
+                K.post.append("    %s b%d = sdqlrt::block_sum(%s);" % (CT[f[1]], j, f[3]))
+                K.post.append("    if (threadIdx.x == 0) c.part[%s + %d * (long long)gridDim.x + blockIdx.x] = %s;" %
+                              (part, j, "b%d" % j if f[1] == "f64" else "__longlong_as_double(b%d)" % j))
+            K.post.append("    if (sdqlrt::last_block(c.cnt + %d)) {" % cnt)
+            for j, f in enumerate(self.fields):
+                if f[1] == "f64":
+                    K.post.append("        double s%d = 0; for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) "
+                                  "s%d += c.part[%s + %d * (long long)gridDim.x + b];" % (j, j, part, j))
+                    K.post.append("        s%d = sdqlrt::block_sum(s%d);" % (j, j))
+                    K.post.append("        if (threadIdx.x == 0) c.sc[%d] = s%d;" % (f[2], j))
+                else:
+                    K.post.append("        long long s%d = 0; for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) "
+                                  "s%d += __double_as_longlong(c.part[%s + %d * (long long)gridDim.x + b]);" % (j, j, part, j))
+                    K.post.append("        s%d = sdqlrt::block_sum(s%d);" % (j, j))
+                    K.post.append("        if (threadIdx.x == 0) c.sc[%d] = __longlong_as_double(s%d);" % (f[2], j))
+            K.post.append("    }")
+            K.post.append("}")
+        for s in self.sub.values():
+            s.finish()
+
+        def dev(f):
+            if f[1] == "f64":
+                return SScalar("f64", "c.sc[%d]" % f[2])
+            return SScalar("i64", "__double_as_longlong(c.sc[%d])" % f[2])
+        if self.scalar:
+            return dev(self.fields[0])
+        out = [(f[0], dev(f)) for f in self.fields]
+        out += [(n, STable(s.t)) for n, s in self.sub.items()]
+        return SRec(out)
+
+
+def unwrap(v):
+    return v.value() if isinstance(v, SLookup) else v
+
+
+def is_true(v):
+    return isinstance(v, SScalar) and v.code == "true"
+
+
+class KeyedSink:
+    """shared by BuildSink / GroupSink: FD-minimised, mixed-radix packed keys."""
+
+    def setup_key(self, t, keyval, extra_parts=()):
+        q, K = self.q, self.K
+        leaves = flatten(K, keyval)
+        kept = minimise_key(q, leaves)
+        if not kept:
+            kept = leaves[:1]
+        parts = [q.part_code(K, x) for x in kept] + list(extra_parts)
+        if not t.parts:
+            t.full_arity = len(leaves)
+            t.kept_pos = [i for i, x in enumerate(leaves) if any(x is y for y in kept)]
+            t.leaf_kinds = [leaf_kind(x) for x in kept]
+            kv = unwrap(keyval)
+            if isinstance(kv, (SRec, SRow)):
+                names = [n for n, _ in kv.items(K)]
+                t.key_shape = names if len(names) == len(leaves) else None
+            else:
+                t.key_shape = "scalar"
+            t.parts = [p[1] for p in parts]
+            if any(p[0] == "raw" for p in t.parts) and len(t.parts) > 1:
+                raise CodegenError("%s: key with an unbounded part cannot be packed with other parts" % t.name)
+        elif len(t.parts) != len(parts):
+            raise CodegenError("%s: inconsistent key shapes" % t.name)
+        return [p[0] for p in parts]
+
+    def pack(self, t, codes):
+        K = self.K
+        kk = K.tmp("kk")
+        K.emit("unsigned long long %s = 0; bool %s_ok = true;" % (kk, kk))
+        for j, code in enumerate(codes):
+            K.emit("%s_ok &= sdqlrt::pack_part(%s, c.%s_mn[%d], c.%s_rng[%d], c.%s_mul[%d], %s);" %
+                   (kk, code, t.name, j, t.name, j, t.name, j, kk))
+        return kk
+
+
+class BuildSink(KeyedSink):
+    """A1/A3: assignment ("unique") dictionary: key -> representative source index."""
+
+    def __init__(self, q, K, t):
+        self.q, self.K, self.t = q, K, t
+        t.src = K.src
+
+    def produce(self, d):
+        K, t = self.K, self.t
+        kk = self.pack(t, self.setup_key(t, d.k))
+        K.emit("if (%s_ok) { bool nw; sdqlrt::tbl_upsert(c.%s, %s, (int)%s, nw); }" % (kk, t.name, kk, K.scan_var))
+
+    def finish(self):
+        return STable(self.t)
+
+
+class GroupSink(KeyedSink):
+    """A4: aggregating dictionary (GROUP BY)."""
+
+    def __init__(self, q, K, t, tiered=True):
+        self.q, self.K, self.t = q, K, t
+        t.src = K.src
+        self.tiered = tiered
+        self.tc = None
+
+    def produce(self, d):
+        q, K, t = self.q, self.K, self.t
+        v = unwrap(d.v)
+        extra, inner_leaves = [], None
+        if isinstance(v, SDictLit):  # nested dictionary value
+            inner_leaves = flatten(K, v.k)
+            extra = [q.part_code(K, x) for x in inner_leaves]
+            iv = unwrap(v.v)
+            if is_true(iv):
+                return self.produce_distinct(d, extra)
+            v = iv
+        if isinstance(v, SVecLit):
+            items, t.count_only = [(None, SScalar("i64", "1ll"))], True
+        elif isinstance(v, SScalar):
+            items, t.scalar_value = [(None, v)], True
+        elif isinstance(v, (SRec, SRow)):
+            items = [(n, unwrap(x)) for n, x in v.items(K)]
+        else:
+            raise CodegenError("cannot aggregate a %s" % type(v).__name__)
+        codes = self.setup_key(t, d.k, extra)
+        if inner_leaves is not None and t.inner is None:
+            t.inner = (len(codes) - len(extra), [p[1] for p in extra], inner_leaves)
+            self.tiered = False
+        if not t.fields:
+            for n, x in items:
+                if not isinstance(x, SScalar):
+                    raise CodegenError("cannot aggregate field %s of type %s" % (n, type(x).__name__))
+                t.fields.append((n, "i64" if x.ctype == "bool" else x.ctype))
+            if self.tiered:
+                self._prologue()
+        kk = self.pack(t, codes)
+        K.open_if("%s_ok" % kk)
+        nf = len(t.fields)
+        vals = [cast_to(x, ct) for (n, x), (_, ct) in zip(items, t.fields)]
+        if self.tiered:
+            K.emit("if (TIER == 0) {")
+            for j, (_, ct) in enumerate(t.fields):
+                idx = "((%s * %d + %d) * blockDim.x + threadIdx.x)" % (kk, nf, j)
+                if ct == "f64":
+                    K.emit("    sm[%s] = __double_as_longlong(__longlong_as_double(sm[%s]) + %s);" % (idx, idx, vals[j]))
+                else:
+                    K.emit("    sm[%s] += (unsigned long long)(%s);" % (idx, vals[j]))
+            K.emit("    smrep[%s * blockDim.x + threadIdx.x] = (int)%s;" % (kk, K.scan_var))
+            K.emit("} else if (TIER == 1) {")
+            for j, (_, ct) in enumerate(t.fields):
+                idx = "(%s * %d + %d)" % (kk, nf, j)
+                if ct == "f64":
+                    K.emit("    atomicAdd((double*)&sm[%s], %s);" % (idx, vals[j]))
+                else:
+                    K.emit("    atomicAdd(&sm[%s], (unsigned long long)(%s));" % (idx, vals[j]))
+            K.emit("    smrep[%s] = (int)%s;" % (kk, K.scan_var))
+            K.emit("} else {")
+            K.depth += 1
+        K.emit("bool nw; const int sl = sdqlrt::tbl_upsert(c.%s, %s, (int)%s, nw);" % (t.name, kk, K.scan_var))
+        for j in range(nf):
+            K.emit("sdqlrt::red_add(c.%s_a%d + sl, %s);" % (t.name, j, vals[j]))
+        if self.tiered:
+            K.depth -= 1
+            K.emit("}")
+        K.close()
+
+    def produce_distinct(self, d, inner_parts):
+        """{k: {x: True}} aggregated: a set of (k, x) plus a per-k counter bumped on first insertion (Q16 dictSize)."""
+        q, K, t = self.q, self.K, self.t
+        self.tiered = False
+        if self.tc is None:
+            self.tc = q.new_table("build")
+            self.tc.src = K.src
+            t.fields = [(None, "i64")]
+            t.scalar_value = True
+            t.distinct_of = self.tc
+        tc = self.tc
+        ccodes = self.setup_key(tc, d.k, inner_parts)
+        ocodes = self.setup_key(t, d.k)
+        kc = self.pack(tc, ccodes)
+        K.open_if("%s_ok" % kc)
+        K.emit("bool nwc; sdqlrt::tbl_upsert(c.%s, %s, (int)%s, nwc);" % (tc.name, kc, K.scan_var))
+        K.open_if("nwc")
+        ko = self.pack(t, ocodes)
+        K.emit("bool nw; const int sl = sdqlrt::tbl_upsert(c.%s, %s, (int)%s, nw);" % (t.name, ko, K.scan_var))
+        K.emit("sdqlrt::red_add(c.%s_a0 + sl, 1ll);" % t.name)
+        K.close()
+        K.close()
+
+    def _prologue(self):
+        K, t = self.K, self.t
+        nf = len(t.fields)
+        K.tiered = True
+        K.pre.append("SDQL_EXTERN_SMEM(sm);")
+        K.pre.append("const long long ncap = c.%s.cap;" % t.name)
+        K.pre.append("int* smrep = (int*)(sm + (TIER == 0 ? ncap * %d * blockDim.x : ncap * %d));" % (nf, nf))
+        K.pre.append("if (TIER == 0) { for (long long k = 0; k < ncap * %d; ++k) sm[k * blockDim.x + threadIdx.x] = 0; "
+                     "for (long long k = 0; k < ncap; ++k) smrep[k * blockDim.x + threadIdx.x] = -1; }" % nf)
+        K.pre.append("if (TIER == 1) { for (long long k = threadIdx.x; k < ncap * %d; k += blockDim.x) sm[k] = 0; "
+                     "for (long long k = threadIdx.x; k < ncap; k += blockDim.x) smrep[k] = -1; __syncthreads(); }" % nf)
+        K.smem_nf = nf
+        K.smem_tbl = t.name
+
+    def finish(self):
+        K, t = self.K, self.t
+        if self.tiered and K.tiered and t.fields:
+            nf = len(t.fields)
+            P = K.post
+            P.append("if (TIER == 0) {")
+            P.append("    for (long long k = 0; k < ncap; ++k) {")
+            P.append("        int r = sdqlrt::block_max(smrep[k * blockDim.x + threadIdx.x]);")
+            for j, (_, ct) in enumerate(t.fields):
+                idx = "sm[(k * %d + %d) * blockDim.x + threadIdx.x]" % (nf, j)
+                if ct == "f64":
+                    P.append("        double v%d = sdqlrt::block_sum(__longlong_as_double(%s));" % (j, idx))
+                else:
+                    P.append("        long long v%d = sdqlrt::block_sum((long long)%s);" % (j, idx))
+            P.append("        if (threadIdx.x == 0 && r >= 0) {")
+            P.append("            atomicMax(c.%s.rep + k, r);" % t.name)
+            for j, (_, ct) in enumerate(t.fields):
+                P.append("            sdqlrt::red_add(c.%s_a%d + k, v%d);" % (t.name, j, j))
+            P.append("        }")
+            P.append("    }")
+            P.append("} else if (TIER == 1) {")
+            P.append("    __syncthreads();")
+            P.append("    for (long long k = threadIdx.x; k < ncap; k += blockDim.x) {")
+            P.append("        int r = smrep[k];")
+            P.append("        if (r >= 0) {")
+            P.append("            atomicMax(c.%s.rep + k, r);" % t.name)
+            for j, (_, ct) in enumerate(t.fields):
+                if ct == "f64":
+                    P.append("            sdqlrt::red_add(c.%s_a%d + k, __longlong_as_double(sm[k * %d + %d]));" % (t.name, j, nf, j))
+                else:
+                    P.append("            sdqlrt::red_add(c.%s_a%d + k, (long long)sm[k * %d + %d]);" % (t.name, j, nf, j))
+            P.append("        }")
+            P.append("    }")
+            P.append("}")
+        return STable(t)
+
+
+class ResultSink:
+    """final result set {record -> True}: append rows to SoA output columns (A6 + boundary, gen:871-877)."""
+
+    def __init__(self, q, K):
+        self.q, self.K = q, K
+
+    def produce(self, d):
+        q, K = self.q, self.K
+        key = d.k if isinstance(d, SDictLit) else d
+        if isinstance(key, (SScalar, SStr)):
+            key = SRec([("_", key)])
+        if isinstance(key, SLookup):
+            key = key.value()
+        items = key.items(K)
+        schema, codes = [], []
+        for n, x in items:
+            if isinstance(x, SLookup):
+                x = x.value()
+            kind, code = q.result_field(K, x)
+            schema.append((n, kind))
+            codes.append(code)
+        if q.result_schema is None:
+            q.result_schema = schema
+        elif [s[1] for s in q.result_schema] != [s[1] for s in schema]:
+            raise CodegenError("result rows of different shapes")
+        pos = K.tmp("pos")
+        K.emit("const unsigned long long %s = sdqlrt::append_slot(c.res_count);" % pos)
+        K.open_if("%s < (unsigned long long)c.res_cap" % pos)
+        for j, code in enumerate(codes):
+            K.emit("c.res%d[%s] = %s;" % (j, pos, code))
+        K.close()
+
+    def finish(self):
+        return "RESULT"
+
+
+def minimise_key(q, leaves):
+    """drop key parts that are functionally determined by the remaining ones."""
+    kept = [x for x in leaves if not (isinstance(x, SStr) and x.kind == "const")]
+
+    def closure(parts):
+        det = set()
+        for p in parts:
+            det |= set(p.det)
+            if not p.prov or all(isinstance(t, tuple) and t and t[0] == "col" for t in p.prov):
+                det |= set(p.prov)
+        changed = True
+        while changed:
+            changed = False
+            for tok, deps in q.token_deps.items():
+                if tok not in det and deps is not None and all(d in det for d in deps):
+                    det.add(tok)
+                    changed = True
+        return det
+
+    changed = True
+    while changed:
+        changed = False
+        for i, p in enumerate(kept):
+            others = kept[:i] + kept[i + 1:]
+            if not p.prov:
+                continue
+            if all(isinstance(t, tuple) and t and t[0] == "col" for t in p.prov):
+                continue  # an atom of the scanned row: always by value
+            if p.prov <= closure(others):
+                kept = others
+                changed = True
+                break
+    return kept
+
+
+# =============================================================================================
+# query compiler
+# =============================================================================================
+class Query:
+    def __init__(self, name, args, schemas):
+        self.name, self.args, self.schemas = name, args, schemas
+        self.inputs, self.input_idx = [], {}
+        self.consts, self.const_idx = [], {}
+        self.tables, self.kernels, self.steps = [], [], []
+        self.nsc = 0
+        self.npart = []
+        self.ncnt = 0
+        self.token_deps = {}
+        self.ntok = 0
+        self.result_schema = None
+        self.result_kind = None
+        self.res_cap_expr = "1"
+
+    # -- resources --------------------------------------------------------------------------
+    def input(self, arg, col, rep):
+        k = (arg, col, rep)
+        if k not in self.input_idx:
+            self.input_idx[k] = len(self.inputs)
+            self.inputs.append(k)
+        return self.input_idx[k]
+
+    def const_code(self, arg, col, lit):
+        k = ("strcode", arg, col, lit)
+        if k not in self.const_idx:
+            self.const_idx[k] = len(self.consts)
+            self.consts.append(k)
+        return "c.k%d" % self.const_idx[k]
+
+    def new_scalar(self):
+        self.nsc += 1
+        return self.nsc - 1
+
+    def new_partials(self, nf):
+        off = "c.part_off%d" % len(self.npart)
+        self.npart.append(nf)
+        return off
+
+    def new_counter(self):
+        self.ncnt += 1
+        return self.ncnt - 1
+
+    def new_table(self, kind):
+        t = TableDesc(self, "t%d" % len(self.tables), kind)
+        self.tables.append(t)
+        return t
+
+    def new_token(self, table, keyprov):
+        self.ntok += 1
+        tok = ("lk", table.name, self.ntok)
+        self.token_deps[tok] = keyprov
+        return tok
+
+    def col_kind(self, arg, col):
+        for n, k in self.schemas[arg]:
+            if n == col:
+                return k
+        raise CodegenError("relation '%s' has no column '%s'" % (arg, col))
+
+    # -- column access ------------------------------------------------------------------------
+    def col_value(self, K, row, col):
+        kind = self.col_kind(row.arg, col)
+        on_scan = row.scan and K is not None and K.src == ("rel", row.arg)
+        prov = row.prov if not on_scan else frozenset([("col", row.arg, col, "i")])
+        if isinstance(kind, tuple):
+            s = SStr("ref", arg=row.arg, col=col, row=row.row, scan=on_scan, width=kind[1], prov=prov)
+            if row.keycode == ("ref", row.arg, col, row.row) and row.token is not None:
+                s.det = frozenset([row.token])
+            return s
+        rep = "f64" if kind == "float" else "i32"
+        if on_scan:
+            code = K.scan_col(col, rep)
+        else:
+            code = "sdqlrt::ld1(c.in%d + %s)" % (self.input(row.arg, col, rep), row.row)
+        if rep == "i32":
+            code = "(long long)" + code
+        det = E
+        if row.token is not None and row.keycode == code:
+            det = frozenset([row.token])
+        return SScalar("f64" if rep == "f64" else "i64", code, prov, det,
+                       ("col", self.input(row.arg, col, rep)) if rep == "i32" else None)
+
+    def str_code(self, K, s):
+        if s.kind == "codeval":
+            return s.code
+        if s.kind == "ref":
+            if s.scan:
+                return K.scan_col(s.col, "code")
+            idx = self.input(s.arg, s.col, "code")
+            return "sdqlrt::ld1_code(c.in%d, %s, c.in%d_w)" % (idx, s.row, idx)
+        raise CodegenError("string of kind %s has no dictionary code" % s.kind)
+
+    def str_ptr(self, K, s):
+        if s.kind != "ref":
+            raise CodegenError("pattern functions need a column string")
+        idx = self.input(s.arg, s.col, "bytes")
+        return "(c.in%d + (long long)(%s) * %d)" % (idx, s.row if not s.scan else "i", s.width), s.width
+
+    def part_code(self, K, x):
+        """by-value key part -> (integer C++ expression, stats)."""
+        if isinstance(x, SScalar):
+            if x.ctype == "f64":
+                return "__double_as_longlong(%s)" % x.code, ("raw",)
+            if x.ctype == "bool":
+                return "(long long)(%s)" % x.code, ("range", 0, 1)
+            return x.code, (x.stats or ("raw",))
+        if x.kind in ("ref", "codeval"):
+            return "(long long)" + self.str_code(K, x), ("col", self.input(x.arg, x.col, "code"))
+        if x.kind == "pack":
+            return x.code, ("range", 0, 256 ** x.n - 1)
+        raise CodegenError("unsupported key part")
+
+    def result_field(self, K, x):
+        if isinstance(x, SScalar):
+            if x.ctype == "f64":
+                return "f64", "__double_as_longlong(%s)" % x.code
+            return ("bool" if x.ctype == "bool" else "i64"), "(long long)(%s)" % x.code
+        if x.kind == "ref":
+            self.host_strings.add((x.arg, x.col))
+            return "str:ref:%s:%s" % (x.arg, x.col), "(long long)(%s)" % (x.row if not x.scan else "i")
+        if x.kind == "codeval":
+            return "str:code:%s:%s" % (x.arg, x.col), "(long long)(%s)" % x.code
+        if x.kind == "pack":
+            return "str:pack:%d" % x.n, x.code
+        if x.kind == "const":
+            return "str:const:" + x.value, "0ll"
+        raise CodegenError("unsupported result field")
+
+    # =========================================================================================
+    # evaluation
+    # =========================================================================================
+    def compile(self, root):
+        self.host_strings = set()
+        env = {}
+        for a in self.args:
+            env[frontend_dataset(a)] = ("rel", a)
+        self.top(root, env)
+        return self
+
+    def top(self, e, env):
+        """host-level let chain."""
+        while True:
+            if not isinstance(e, ir.LetExpr):
+                raise CodegenError("expected a let chain at the top level")
+            if e.varExpr.name == "out":
+                return self.finish_result(self.top_value(e.valExpr, env, True), env)
+            is_res = (isinstance(e.bodyExpr, ir.LetExpr) and e.bodyExpr.varExpr.name == "out"
+                      and isinstance(e.bodyExpr.valExpr, ir.VarExpr) and e.bodyExpr.valExpr.name == e.varExpr.name)
+            env = dict(env)
+            env[e.varExpr.name] = self.top_value(e.valExpr, env, is_res)
+            e = e.bodyExpr
+
+    def top_value(self, e, env, is_res=False):
+        if isinstance(e, ir.SumExpr):
+            return self.compile_sum(e, env, is_res)
+        if isinstance(e, ir.LetExpr):
+            env = dict(env)
+            env[e.varExpr.name] = self.top_value(e.valExpr, env)
+            return self.top_value(e.bodyExpr, env, is_res)
+        return self.ev(e, env, None)
+
+    def finish_result(self, v, env):
+        if v == "RESULT":
+            self.result_kind = "rows"
+            return
+        K = Kernel(self, "%s_fin" % self.name, ("one",))
+        if isinstance(v, SScalar):
+            self.result_kind = "f64" if v.ctype == "f64" else "i64"
+            self.result_schema = [("_", self.result_kind)]
+            K.emit("c.res0[0] = %s; *c.res_count = 1;" %
+                   ("__double_as_longlong(%s)" % v.code if v.ctype == "f64" else "(long long)(%s)" % v.code))
+            self.res_cap_expr = "1"
+        elif isinstance(v, SDictLit):
+            self.result_kind = "rows"
+            ResultSink(self, K).produce(v)
+            self.res_cap_expr = "1"
+        elif isinstance(v, STable):
+            # a dictionary that is returned as is: rows = key fields ++ value fields
+            return self.materialise_table(v.desc)
+        else:
+            raise CodegenError("unsupported result value %s" % type(v).__name__)
+        self.add_kernel(K)
+
+    def materialise_table(self, t):
+        K = Kernel(self, "%s_fin" % self.name, ("tbl", t))
+        elem = SPair(t.key_at(K, "i"), t.value_at(K, "i", None))
+        key = elem.k
+        fields = []
+        if isinstance(key, (SRec, SRow)):
+            fields += key.items(K)
+        else:
+            fields.append(("key", key))
+        if isinstance(elem.v, (SRec, SRow)):
+            fields += elem.v.items(K)
+        elif isinstance(elem.v, SScalar) and elem.v.code != "true":
+            fields.append(("value", elem.v))
+        self.result_kind = "rows"
+        ResultSink(self, K).produce(SRec(fields))
+        self.res_cap_expr = "c.%s.cap" % t.name
+        self.add_kernel(K)
+
+    def add_kernel(self, K):
+        self.kernels.append(K)
+        self.steps.append(("launch", K))
+
+    # -- sums -----------------------------------------------------------------------------------
+    def compile_sum(self, S, env, is_res=False):
+        src = self.ev(S.dictExpr, env, None)
+        if isinstance(src, tuple) and src[0] == "rel":
+            K = Kernel(self, "%s_k%d" % (self.name, len(self.kernels)), src)
+            elem = SPair(SRow(self, src[1], "i", scan=True), TRUE)
+            cap = "c.n_%s" % src[1]
+        elif isinstance(src, STable):
+            t = src.desc
+            K = Kernel(self, "%s_k%d" % (self.name, len(self.kernels)), ("tbl", t))
+            tok = ("it", K.name)
+            self.token_deps[tok] = None
+            elem = None
+            cap = "c.%s.cap" % t.name
+        else:
+            raise CodegenError("cannot sum over %s" % type(src).__name__)
+        K.S, K.is_res = S, is_res
+        K.src_cap = cap
+        if elem is None:
+            t = src.desc
+            key = mark_iter(self, K, t)
+            elem = key
+        env2 = dict(env)
+        env2[S.varExpr.name] = elem
+        self.run_body(S.bodyExpr, env2, K)
+        if K.sink is None:
+            raise CodegenError("sum body never produces a value")
+        out = K.sink.finish()
+        if out == "RESULT":
+            self.res_cap_expr = cap
+        self.add_kernel(K)
+        return out
+
+    def make_sink(self, K, v):
+        S = K.S
+        if isinstance(v, SDictLit):
+            val = v.v.value() if isinstance(v.v, SLookup) else v.v
+            is_set = isinstance(val, SScalar) and val.code == "true"
+            if K.is_res and is_set:
+                return ResultSink(self, K)
+            dense = S.dictType.startswith("dense_array")
+            if isinstance(val, SVecLit) or isinstance(val, SDictLit):
+                return GroupSink(self, K, self.new_table("agg"))
+            if S.isAssignmentSum or (dense and not isinstance(val, SVecLit)):
+                t = self.new_table("build")
+                return BuildSink(self, K, t)
+            return GroupSink(self, K, self.new_table("agg"))
+        if isinstance(v, (SScalar, SRec)):
+            return ReduceSink(self, K, v)
+        raise CodegenError("sum body produces unsupported value %s" % type(v).__name__)
+
+    def run_body(self, e, env, K):
+        if isinstance(e, ir.IfExpr):
+            trivial_else = isinstance(e.elseBodyExpr, ir.EmptyDicConsExpr) or (
+                isinstance(e.elseBodyExpr, ir.ConstantExpr) and e.elseBodyExpr.value in (None, 0, 0.0, False))
+            if not trivial_else:
+                raise CodegenError("if/else with a non-zero else branch at statement level is not supported")
+            n = 0
+            for conj in and_chain(e.condExpr):
+                c = self.ev(conj, env, K)
+                K.open_if(as_bool(c))
+                n += 1
+            self.run_body(e.thenBodyExpr, env, K)
+            for _ in range(n):
+                K.close()
+            return
+        if isinstance(e, ir.SumExpr):  # nested sum over the inner dictionary of a lookup (Q12)
+            return self.nested_sum(e, env, K)
+        if isinstance(e, (ir.EmptyDicConsExpr,)) or (isinstance(e, ir.ConstantExpr) and e.value is None):
+            return
+        v = self.ev(e, env, K)
+        if K.sink is None:
+            K.sink = self.make_sink(K, v)
+            if isinstance(K.sink, (BuildSink, GroupSink)):
+                self.bind_table_fns(K, K.sink.t, e, env)
+        K.sink.produce(v)
+        if isinstance(K.sink, ReduceSink) and isinstance(e, ir.RecConsExpr):
+            for name, fe in e.initialPairs:
+                sub = K.sink.sub.get(name)
+                if sub is not None and sub.t.key_fn is None:
+                    self.bind_table_fns(K, sub.t, fe, env)
+
+    def bind_table_fns(self, K, t, e, env):
+        """closures that re-evaluate the key / value expression of a produced {k: v} at a given source index."""
+        S = K.S
+        q = self
+        var = S.varExpr.name
+        if not isinstance(e, ir.DicConsExpr):
+            return
+        kexpr, vexpr = e.initialPairs[0]
+
+        def elem_at(K2, idx, prov):
+            if K.src[0] == "rel":
+                return SPair(SRow(q, K.src[1], idx, scan=False, prov=prov), TRUE)
+            st = K.src[1]
+            return SPair(st.key_at(K2, idx, prov), st.value_at(K2, idx, None, prov=prov))
+
+        def key_fn(K2, idx, prov=E):
+            env2 = dict(env)
+            env2[var] = elem_at(K2, idx, prov)
+            return q.ev(kexpr, env2, K2)
+
+        def val_fn(K2, idx, prov=E):
+            env2 = dict(env)
+            env2[var] = elem_at(K2, idx, prov)
+            return q.ev(vexpr, env2, K2)
+
+        t.key_fn, t.val_fn = key_fn, val_fn
+
+    def nested_sum(self, S, env, K):
+        d = self.ev(S.dictExpr, env, K)
+        if not (isinstance(d, SLookup) and d.table.inner is not None):
+            raise CodegenError("nested sum over something that is not a dictionary-valued lookup")
+        t = d.table
+        n_outer, inner_stats, inner_leaves = t.inner
+        if len(inner_stats) != 1 or inner_stats[0][0] != "col":
+            raise CodegenError("nested dictionaries need a single dictionary-coded inner key")
+        idx = inner_stats[0][1]
+        cv = K.tmp("cv")
+        K.open_block("for (long long %s = c.%s_mn[%d]; %s < c.%s_mn[%d] + c.%s_rng[%d]; ++%s)" %
+                     (cv, t.name, n_outer, cv, t.name, n_outer, t.name, n_outer, cv))
+        kk = K.tmp("kk")
+        K.emit("unsigned long long %s = %s_outer + (unsigned long long)(%s - c.%s_mn[%d]) * (unsigned long long)c.%s_mul[%d];" %
+               (kk, d.slot, cv, t.name, n_outer, t.name, n_outer))
+        sl = K.let("int", "sdqlrt::tbl_find(c.%s, %s, %s_outer_ok)" % (t.name, kk, d.slot))
+        K.open_if("%s >= 0" % sl)
+        leaf = inner_leaves[0]
+        if isinstance(leaf, SStr):
+            kval = SStr("codeval", arg=leaf.arg, col=leaf.col, code=cv)
+        else:
+            kval = SScalar("i64", cv, stats=inner_stats[0])
+        vals = [SScalar(ct, "sdqlrt::ld1(c.%s_a%d + %s)" % (t.name, j, sl)) for j, (_, ct) in enumerate(t.fields)]
+        env2 = dict(env)
+        env2[S.varExpr.name] = SPair(kval, vals[0] if (t.scalar_value or t.count_only) else
+                                     SRec([(n, v) for (n, _), v in zip(t.fields, vals)]))
+        self.run_body(S.bodyExpr, env2, K)
+        K.close()
+        K.close()
+
+    # -- lookups ----------------------------------------------------------------------------------
+    def lookup(self, K, t, keyval):
+        if K is None:
+            raise CodegenError("dictionary lookup outside of a sum body")
+        leaves = flatten(K, keyval)
+        n_expected = len(t.parts) if t.inner is None else t.inner[0]
+        # the probe key has the build key's *full* shape; keep the positions the build kept by value
+        if len(leaves) != n_expected:
+            full = getattr(t, "full_arity", None)
+            if full is not None and len(leaves) == full:
+                leaves = [leaves[i] for i in t.kept_pos]
+            else:
+                raise CodegenError("%s: lookup key has %d parts, table key has %d" % (t.name, len(leaves), n_expected))
+        codes = [self.part_code(K, x)[0] for x in leaves]
+        ckey = ("lookup", t.name, tuple(codes))
+        hit = None
+        for scope in K.cse:
+            if ckey in scope:
+                hit = scope[ckey]
+        if hit is None:
+            kk = K.tmp("lk")
+            K.emit("unsigned long long %s = 0; bool %s_ok = true;" % (kk, kk))
+            for j, code in enumerate(codes):
+                K.emit("%s_ok &= sdqlrt::pack_part(%s, c.%s_mn[%d], c.%s_rng[%d], c.%s_mul[%d], %s);" %
+                       (kk, code, t.name, j, t.name, j, t.name, j, kk))
+            keyprov = frozenset().union(*[x.prov for x in leaves]) if leaves else E
+            tok = self.new_token(t, keyprov if all(x.prov for x in leaves) else None)
+            if t.inner is not None:
+                K.emit("const unsigned long long %s_outer = %s; const bool %s_outer_ok = %s_ok;" % (kk, kk, kk, kk))
+                sl = kk
+            else:
+                sl = K.tmp("sl")
+                K.emit("const int %s = sdqlrt::tbl_find(c.%s, %s, %s_ok);" % (sl, t.name, kk, kk))
+            hit = (sl, tok)
+            K.cse[-1][ckey] = hit
+        sl, tok = hit
+        lk = SLookup(K, t, sl, tok)
+        if t.inner is not None:
+            # `d[k] != None` on a dictionary-valued entry: subsumed by iterating the inner dictionary, which
+            # yields nothing when no (k, *) entry exists (the only use in the workload is joinProbe, Q12)
+            lk.found = "true"
+        return lk
+
+    # -- expressions ---------------------------------------------------------------------------
+    def ev(self, e, env, K):
+        m = getattr(self, "ev_" + type(e).__name__)
+        return m(e, env, K)
+
+    def ev_ConstantExpr(self, e, env, K):
+        v = e.value
+        if v is None:
+            return SNone()
+        if isinstance(v, bool):
+            return SScalar("bool", "true" if v else "false")
+        if isinstance(v, int):
+            return SScalar("i64", "%dll" % v, stats=("range", v, v))
+        if isinstance(v, float):
+            return SScalar("f64", lit_f64(v))
+        return SStr("const", value=v)
+
+    def ev_VarExpr(self, e, env, K):
+        if e.name not in env:
+            raise CodegenError("unbound variable %s" % e.name)
+        return env[e.name]
+
+    def ev_LetExpr(self, e, env, K):
+        env = dict(env)
+        env[e.varExpr.name] = self.ev(e.valExpr, env, K) if K is not None else self.top_value(e.valExpr, env)
+        return self.ev(e.bodyExpr, env, K)
+
+    def ev_SumExpr(self, e, env, K):
+        if K is None:
+            return self.compile_sum(e, env)
+        raise CodegenError("nested sum in expression position")
+
+    def ev_PairAccessExpr(self, e, env, K):
+        p = self.ev(e.pairExpr, env, K)
+        if not isinstance(p, SPair):
+            raise CodegenError("[%d] on a non-pair" % e.index)
+        return p.k if e.index == 0 else p.v
+
+    def ev_RecAccessExpr(self, e, env, K):
+        r = self.ev(e.recExpr, env, K)
+        if isinstance(r, SLookup):
+            r = r.value()
+        if isinstance(r, (SRec, SRow)):
+            return r.field(K, e.name)
+        raise CodegenError("field access .%s on %s" % (e.name, type(r).__name__))
+
+    def ev_RecConsExpr(self, e, env, K):
+        return SRec([(n, self.ev(x, env, K)) for n, x in e.initialPairs])
+
+    def ev_ConcatExpr(self, e, env, K):
+        a, b = self.ev(e.rec1, env, K), self.ev(e.rec2, env, K)
+        out = []
+        for r in (a, b):
+            if isinstance(r, SLookup):
+                r = r.value()
+            if not isinstance(r, (SRec, SRow)):
+                raise CodegenError("concat needs records")
+            out += r.items(K)
+        return SRec(out)
+
+    def ev_DicConsExpr(self, e, env, K):
+        k, v = e.initialPairs[0]
+        return SDictLit(self.ev(k, env, K), self.ev(v, env, K))
+
+    def ev_EmptyDicConsExpr(self, e, env, K):
+        return SNone()
+
+    def ev_VecConsExpr(self, e, env, K):
+        return SVecLit(self.ev(e.exprList[0], env, K))
+
+    def ev_DicLookupExpr(self, e, env, K):
+        d = self.ev(e.dicExpr, env, K)
+        if not isinstance(d, STable):
+            raise CodegenError("lookup in something that is not a dictionary (%s)" % type(d).__name__)
+        return self.lookup(K, d.desc, self.ev(e.keyExpr, env, K))
+
+    def ev_IfExpr(self, e, env, K):
+        c = self.ev(e.condExpr, env, K)
+        a, b = self.ev(e.thenBodyExpr, env, K), self.ev(e.elseBodyExpr, env, K)
+        a = a.value() if isinstance(a, SLookup) else a
+        b = b.value() if isinstance(b, SLookup) else b
+        if isinstance(a, SScalar) and isinstance(b, SScalar):
+            ct = "f64" if "f64" in (a.ctype, b.ctype) else a.ctype
+            return SScalar(ct, "(%s ? %s : %s)" % (as_bool(c), cast_to(a, ct), cast_to(b, ct)), a.prov | b.prov | c.prov)
+        raise CodegenError("conditional expression over non-scalars")
+
+    def _arith(self, e, env, K, op):
+        a, b = self.ev(e.op1Expr, env, K), self.ev(e.op2Expr, env, K)
+        a = a.value() if isinstance(a, SLookup) else a
+        b = b.value() if isinstance(b, SLookup) else b
+        if not (isinstance(a, SScalar) and isinstance(b, SScalar)):
+            raise CodegenError("arithmetic on non-scalars")
+        prov = a.prov | b.prov
+        if a.ctype == "bool" and b.ctype == "bool" and op in "*+":  # gen:69-70, 78-79
+            return SScalar("bool", "(%s %s %s)" % (a.code, "&&" if op == "*" else "||", b.code), prov)
+        ct = "f64" if "f64" in (a.ctype, b.ctype) else "i64"
+        return SScalar(ct, "(%s %s %s)" % (cast_to(a, ct), op, cast_to(b, ct)), prov)
+
+    def ev_AddExpr(self, e, env, K):
+        return self._arith(e, env, K, "+")
+
+    def ev_SubExpr(self, e, env, K):
+        return self._arith(e, env, K, "-")
+
+    def ev_MulExpr(self, e, env, K):
+        return self._arith(e, env, K, "*")
+
+    def ev_DivExpr(self, e, env, K):
+        return self._arith(e, env, K, "/")
+
+    def ev_CompareExpr(self, e, env, K):
+        a, b = self.ev(e.leftExpr, env, K), self.ev(e.rightExpr, env, K)
+        op = e.compareType
+        if isinstance(a, SNone) or isinstance(b, SNone):  # gen:86-91, 147-153
+            lk = b if isinstance(a, SNone) else a
+            if not isinstance(lk, SLookup):
+                raise CodegenError("comparison with None needs a dictionary lookup")
+            if lk.found is None:
+                raise CodegenError("None test on a nested dictionary lookup")
+            return SScalar("bool", lk.found if op == CS.NE else "(!%s)" % lk.found)
+        a = a.value() if isinstance(a, SLookup) else a
+        b = b.value() if isinstance(b, SLookup) else b
+        sym = {CS.EQ: "==", CS.NE: "!=", CS.LT: "<", CS.LTE: "<=", CS.GT: ">", CS.GTE: ">="}[op]
+        if isinstance(a, SStr) or isinstance(b, SStr):
+            return self.str_compare(K, a, b, sym)
+        prov = a.prov | b.prov
+        if a.ctype == "bool" or b.ctype == "bool":
+            return SScalar("bool", "((bool)(%s) %s (bool)(%s))" % (a.code, sym, b.code), prov)
+        ct = "f64" if "f64" in (a.ctype, b.ctype) else "i64"
+        return SScalar("bool", "(%s %s %s)" % (cast_to(a, ct), sym, cast_to(b, ct)), prov)
+
+    def str_compare(self, K, a, b, sym):
+        if sym not in ("==", "!="):
+            raise CodegenError("only == / != on strings")
+        if isinstance(a, SStr) and a.kind == "const":
+            a, b = b, a
+        if not (isinstance(a, SStr) and isinstance(b, SStr)):
+            raise CodegenError("string compared with a non-string")
+        if b.kind == "const":
+            if a.kind == "pack":
+                v = 0
+                bs = b.value.encode("ascii")[:a.n].ljust(a.n, b"\0")
+                for ch in bs:
+                    v = (v << 8) | ch
+                return SScalar("bool", "(%s %s %dll)" % (a.code, sym, v), a.prov)
+            if a.kind == "const":
+                return SScalar("bool", "true" if (a.value == b.value) == (sym == "==") else "false")
+            return SScalar("bool", "(%s %s %s)" % (self.str_code(K, a), sym, self.const_code(a.arg, a.col, b.value)), a.prov)
+        if (a.arg, a.col) == (b.arg, b.col):
+            return SScalar("bool", "(%s %s %s)" % (self.str_code(K, a), sym, self.str_code(K, b)), a.prov | b.prov)
+        raise CodegenError("comparison of strings from different columns is not supported")
+
+    def ev_ExtFuncExpr(self, e, env, K):
+        s = e.symbol
+        a = self.ev(e.inp1, env, K)
+        a = a.value() if isinstance(a, SLookup) and s != XF.DictSize else a
+        if s == XF.ExtractYear:  # gen:623-624
+            st = ("year", a.stats[1]) if a.stats and a.stats[0] == "col" else None
+            return SScalar("i64", "(%s / 10000)" % a.code, a.prov, E, st)
+        if s == XF.DictSize:
+            if isinstance(a, SLookup) and a.table.count_only:
+                return SScalar("i64", "(%s ? sdqlrt::ld1(c.%s_a0 + (%s < 0 ? 0 : %s)) : 0ll)" %
+                               (a.found, a.table.name, a.slot, a.slot))
+            if isinstance(a, SScalar):   # value of a distinct-count table (Q16)
+                return a
+            raise CodegenError("dictSize of an unsupported value")
+        if s == XF.StringContains:
+            pat, subj = a, self.ev(e.inp3, env, K)
+            ptr, w = self.str_ptr(K, subj)
+            return SScalar("bool", "(sdqlrt::str_find(%s, %d, %s, %d) >= 0)" % (ptr, w, cstr(pat.value), len(pat.value)), subj.prov)
+        b = self.ev(e.inp2, env, K)
+        if s in (XF.StartsWith, XF.EndsWith, XF.FirstIndex):
+            if not (isinstance(b, SStr) and b.kind == "const"):
+                raise CodegenError("pattern must be a string constant")
+            ptr, w = self.str_ptr(K, a)
+            fn = {XF.StartsWith: "str_starts", XF.EndsWith: "str_ends", XF.FirstIndex: "str_find"}[s]
+            code = "sdqlrt::%s(%s, %d, %s, %d)" % (fn, ptr, w, cstr(b.value), len(b.value))
+            if s == XF.FirstIndex:
+                return SScalar("i64", "(long long)" + K.let("int", code), a.prov)
+            return SScalar("bool", code, a.prov)
+        if s == XF.SubStr:
+            c3 = self.ev(e.inp3, env, K)
+            lo, hi = int(e.inp2.value), int(e.inp3.value)
+            ptr, w = self.str_ptr(K, a)
+            n = hi - lo + 1
+            if n > 7:
+                raise CodegenError("substr longer than 7 characters")
+            return SStr("pack", n=n, code="sdqlrt::str_pack(%s, %d, %d)" % (ptr, lo, n), prov=a.prov)
+        raise CodegenError("unsupported external function %s" % s)
+
+
+def frontend_dataset(a):
+    return "db->" + a + "_dataset"
+
+
+def and_chain(e):
+    """flatten a * b * c (logical and after comp:277-292) into conjuncts, left to right."""
+    if isinstance(e, ir.MulExpr):
+        return and_chain(e.op1Expr) + and_chain(e.op2Expr)
+    return [e]
+
+
+def as_bool(v):
+    if isinstance(v, SLookup):
+        v = v.value()
+    if not isinstance(v, SScalar):
+        raise CodegenError("condition is not a scalar")
+    return v.code if v.ctype == "bool" else "(%s != 0)" % v.code
+
+
+def mark_iter(q, K, t):
+    """element of a table-sourced kernel: p[0] = key (re-evaluated at the slot's representative), p[1] = value."""
+    tok = ("it", K.name)
+    prov = frozenset([tok])
+    key = t.key_at(K, "i", prov) if t.key_fn is not None else None
+    if t.inner is not None:
+        raise CodegenError("iteration over a nested dictionary is only supported through dictSize / inner sums")
+    val = t.value_at(K, "i", None, prov=prov)
+    # the by-value part of the table key determines the slot (single-part keys)
+    if key is not None and getattr(t, "key_shape", None) is not None and len(t.kept_pos) == 1:
+        if t.key_shape == "scalar":
+            key.det = key.det | frozenset([tok])
+        else:
+            nm = t.key_shape[t.kept_pos[0]]
+            x = key.fields[nm]
+            if not callable(x):
+                x.det = x.det | frozenset([tok])
+    return SPair(key, val)
+
+
+# =============================================================================================
+# module text
+# =============================================================================================
+def _stats_exprs(st):
+    """-> (min expr, range expr) in generated host code for a key-part statistics tuple."""
+    if st[0] == "col":
+        return "a->cols[%d].min" % st[1], "(a->cols[%d].max - a->cols[%d].min + 1)" % (st[1], st[1])
+    if st[0] == "year":
+        return "(a->cols[%d].min / 10000)" % st[1], "(a->cols[%d].max / 10000 - a->cols[%d].min / 10000 + 1)" % (st[1], st[1])
+    if st[0] == "range":
+        return "%dll" % st[1], "%dll" % (st[2] - st[1] + 1)
+    return "0ll", "-1ll"
+
+
+def render_query(q):
+    """-> CUDA text of one query: context struct, kernels, host driver."""
+    n = q.name
+    L = []
+    ity = {"i32": "const int*", "f64": "const double*", "code": "const void*", "bytes": "const unsigned char*"}
+    L.append("// " + "=" * 100)
+    L.append("// %s" % n)
+    L.append("// " + "=" * 100)
+    L.append("struct %s_ctx {" % n)
+    for i, (arg, col, rep) in enumerate(q.inputs):
+        L.append("    %s in%d;  // %s.%s (%s)" % (ity[rep], i, arg, col, rep))
+        if rep == "code":
+            L.append("    int in%d_w;" % i)
+    for a in q.args:
+        L.append("    long long n_%s;" % a)
+    for i, k in enumerate(q.consts):
+        L.append("    long long k%d;  // %s" % (i, "/".join(str(x) for x in k)))
+    for t in q.tables:
+        P = max(1, len(t.parts))
+        L.append("    sdqlrt::Tbl %s; long long %s_mn[%d], %s_rng[%d], %s_mul[%d];" % (t.name, t.name, P, t.name, P, t.name, P))
+        for j, (_, ct) in enumerate(t.fields):
+            L.append("    %s* %s_a%d;" % (CT[ct], t.name, j))
+    L.append("    double* sc; double* part; unsigned* cnt;")
+    for i in range(len(q.npart)):
+        L.append("    long long part_off%d;" % i)
+    L.append("    unsigned long long* res_count; long long res_cap;")
+    for j in range(len(q.result_schema or [])):
+        L.append("    long long* res%d;" % j)
+    L.append("};")
+    L.append("")
+    for K in q.kernels:
+        L.append(K.render())
+        L.append("")
+    # ---- host driver ----
+    nres = len(q.result_schema or [])
+    L.append("static int %s_run(sdqlb200_args* a) {" % n)
+    L.append("    if (a->ncols != %d || a->nargs != %d || a->nconsts != %d)" % (len(q.inputs), len(q.args), len(q.consts)))
+    L.append("        return sdqlhost::fail(SDQLB200_E_ARG, \"%s: expected %d inputs / %d args / %d consts\");" %
+             (n, len(q.inputs), len(q.args), len(q.consts)))
+    L.append("    %s_ctx c; memset(&c, 0, sizeof c);" % n)
+    L.append("    sdqlhost::Arena ar(a->workspace, a->workspace_bytes);")
+    L.append("    const int sms = sdqlhost_sms();")
+    ckind = {"i32": "SDQLB200_I32", "f64": "SDQLB200_F64", "code": "SDQLB200_CODE", "bytes": "SDQLB200_BYTES"}
+    for i, (arg, col, rep) in enumerate(q.inputs):
+        L.append("    if (a->cols[%d].kind != %s) return sdqlhost::fail(SDQLB200_E_ARG, \"%s: input %d (%s.%s) must be %s\");" %
+                 (i, ckind[rep], n, i, arg, col, rep))
+        L.append("    c.in%d = (%s)a->cols[%d].data;" % (i, ity[rep], i))
+        if rep == "code":
+            L.append("    c.in%d_w = a->cols[%d].width;" % (i, i))
+    for i, ar_ in enumerate(q.args):
+        L.append("    c.n_%s = a->nrows[%d];" % (ar_, i))
+    for i in range(len(q.consts)):
+        L.append("    c.k%d = a->consts[%d];" % (i, i))
+    nt = len(q.tables)
+    L.append("    unsigned long long ff_off[%d], ff_len[%d];" % (max(1, nt), max(1, nt)))
+    for ti, t in enumerate(q.tables):
+        P = len(t.parts)
+        if P == 0:
+            raise CodegenError("%s: table %s was never keyed" % (n, t.name))
+        mns = ", ".join(_stats_exprs(s)[0] for s in t.parts)
+        rgs = ", ".join(_stats_exprs(s)[1] for s in t.parts)
+        src = "c.n_%s" % t.src[1] if t.src[0] == "rel" else "c.%s.cap" % t.src[1].name
+        L.append("    {")
+        L.append("        long long mn[%d] = {%s}, rng[%d] = {%s};" % (P, mns, P, rgs))
+        L.append("        unsigned long long u0 = ar.used;")
+        L.append("        if (!sdqlhost::size_table(&c.%s, %d, mn, rng, %s, c.%s_mn, c.%s_rng, c.%s_mul, ar))" %
+                 (t.name, P, src, t.name, t.name, t.name))
+        L.append("            return sdqlhost::fail(SDQLB200_E_ARG, \"%s: key domain of %s does not fit 63 bits\");" % (n, t.name))
+        L.append("        ff_off[%d] = u0; ff_len[%d] = ar.used - u0;" % (ti, ti))
+        for j, (_, ct) in enumerate(t.fields):
+            L.append("        c.%s_a%d = ar.alloc<%s>(c.%s.cap);" % (t.name, j, CT[ct], t.name))
+        L.append("    }")
+    L.append("    c.sc = ar.alloc<double>(%d); c.cnt = ar.alloc<unsigned>(%d);" % (max(1, q.nsc), max(1, q.ncnt)))
+    # grids
+    for K in q.kernels:
+        if K.src[0] == "rel":
+            L.append("    const long long w_%s = (c.n_%s + 3) / 4;" % (K.name, K.src[1]))
+        elif K.src[0] == "tbl":
+            L.append("    const long long w_%s = c.%s.cap;" % (K.name, K.src[1].name))
+        else:
+            L.append("    const long long w_%s = 1;" % K.name)
+        L.append("    int g_%s = sdqlhost::grid_for(w_%s, 8, sms);" % (K.name, K.name))
+    L.append("    long long npart = 0;")
+    pi = 0
+    for K in q.kernels:
+        if isinstance(K.sink, ReduceSink) and K.sink.fields:
+            L.append("    c.part_off%d = npart; npart += %dll * g_%s;" % (pi, len(K.sink.fields), K.name))
+            pi += 1
+    L.append("    c.part = ar.alloc<double>(npart);")
+    L.append("    c.res_count = ar.alloc<unsigned long long>(1);")
+    L.append("    const unsigned long long zero_end = ar.used;")
+    L.append("    c.res_cap = %s; if (c.res_cap < 1) c.res_cap = 1;" % q.res_cap_expr)
+    for j in range(nres):
+        L.append("    c.res%d = ar.alloc<long long>(c.res_cap);" % j)
+    L.append("    a->workspace_needed = ar.used;")
+    L.append("    if (!ar.ok()) return sdqlhost::fail(SDQLB200_E_WORKSPACE, \"%s: workspace of %%llu bytes needed\", ar.used);" % n)
+    L.append("    cudaStream_t st = (cudaStream_t)a->stream;")
+    L.append("    SDQL_CUDA(cudaEventRecord(sdqlhost_ev(0), st));")
+    L.append("    SDQL_CUDA(cudaMemsetAsync(a->workspace, 0, zero_end, st));")
+    for ti in range(nt):
+        L.append("    SDQL_CUDA(cudaMemsetAsync((char*)a->workspace + ff_off[%d], 0xFF, ff_len[%d], st));" % (ti, ti))
+    L.append("    int launches = 0;")
+    for K in q.kernels:
+        if K.tiered:
+            nf, tn = K.smem_nf, K.smem_tbl
+            L.append("    {")
+            L.append("        const long long cap = c.%s.cap; int tier = 2; size_t smem = 0;" % tn)
+            L.append("        if (c.%s.direct && cap * %d <= 32) { tier = 0; smem = (size_t)cap * (%d * 8 + 4) * sdqlrt::kBlock; }" % (tn, nf, nf))
+            L.append("        else if (c.%s.direct && cap * (%d * 8 + 4) <= 65536) { tier = 1; smem = (size_t)cap * (%d * 8 + 4); }" % (tn, nf, nf))
+            L.append("        if (tier == 0) {")
+            L.append("            SDQL_CUDA(cudaFuncSetAttribute(%s<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));" % K.name)
+            L.append("            int cps = (int)(200000 / (smem + 1024)); if (cps < 1) cps = 1; if (cps > 8) cps = 8;")
+            L.append("            g_%s = sdqlhost::grid_for(w_%s, cps, sms);" % (K.name, K.name))
+            L.append("            SDQL_LAUNCH(%s<0>, g_%s, sdqlrt::kBlock, smem, st, c);" % (K.name, K.name))
+            L.append("        } else if (tier == 1) {")
+            L.append("            SDQL_CUDA(cudaFuncSetAttribute(%s<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));" % K.name)
+            L.append("            int cps = (int)(200000 / (smem + 1024)); if (cps < 1) cps = 1; if (cps > 8) cps = 8;")
+            L.append("            g_%s = sdqlhost::grid_for(w_%s, cps, sms);" % (K.name, K.name))
+            L.append("            SDQL_LAUNCH(%s<1>, g_%s, sdqlrt::kBlock, smem, st, c);" % (K.name, K.name))
+            L.append("        } else {")
+            L.append("            SDQL_LAUNCH(%s<2>, g_%s, sdqlrt::kBlock, 0, st, c);" % (K.name, K.name))
+            L.append("        }")
+            L.append("        a->tier = tier;")
+            L.append("    }")
+        else:
+            L.append("    SDQL_LAUNCH(%s, g_%s, sdqlrt::kBlock, 0, st, c);" % (K.name, K.name))
+        L.append("    SDQL_CUDA(cudaGetLastError()); ++launches;")
+    L.append("    SDQL_CUDA(cudaEventRecord(sdqlhost_ev(1), st));")
+    L.append("    a->launches = launches;")
+    L.append("    long long* rcols[%d] = {%s};" % (max(1, nres), ", ".join("c.res%d" % j for j in range(nres)) or "nullptr"))
+    L.append("    return sdqlhost_fetch(a, st, c.res_count, c.res_cap, %d, rcols);" % nres)
+    L.append("}")
+    L.append("")
+    return "\n".join(L)
+
+
+def manifest_of(q):
+    return {
+        "name": q.name,
+        "args": q.args,
+        "schemas": {a: [[c, list(k) if isinstance(k, tuple) else k] for c, k in q.schemas[a]] for a in q.args},
+        "inputs": [list(k) for k in q.inputs],
+        "consts": [list(k) for k in q.consts],
+        "result_kind": q.result_kind,
+        "result": [list(s) for s in (q.result_schema or [])],
+        "kernels": [{"name": K.name, "source": list(K.src[:1]) + [K.src[1] if K.src[0] == "rel" else (K.src[1].name if K.src[0] == "tbl" else "")],
+                     "scan_cols": [[c, r] for (c, r) in K.scan_cols]} for K in q.kernels],
+    }
+
+
+MODULE_HEAD = r'''// GENERATED by sdqlpy_b200.codegen -- do not edit.  Source workload: %(src)s
+#include "sdqlb200_host.h"
+
+#ifndef SDQLB200_EMU
+static cudaEvent_t g_ev[2];
+static bool g_ev_init = false;
+static cudaEvent_t sdqlhost_ev(int i) {
+    if (!g_ev_init) { cudaEventCreate(&g_ev[0]); cudaEventCreate(&g_ev[1]); g_ev_init = true; }
+    return g_ev[i];
+}
+static int sdqlhost_sms() {
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms < 1) sms = 148; }
+    return sms;
+}
+#endif
+
+// copy the result rows to host buffers (after the query's kernels): 8 bytes for the row count, then count x fields
+static int sdqlhost_fetch(sdqlb200_args* a, cudaStream_t st, unsigned long long* d_count, long long cap, int nf,
+                          long long* const* d_cols) {
+    unsigned long long cnt = 0;
+    SDQL_CUDA(cudaMemcpyAsync(&cnt, d_count, 8, cudaMemcpyDeviceToHost, st));
+    SDQL_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, sdqlhost_ev(0), sdqlhost_ev(1));
+    a->device_ms = ms;
+    if ((long long)cnt > cap) return sdqlhost::fail(SDQLB200_E_ARG, "result overflow: %%llu rows > capacity %%lld", cnt, cap);
+    a->result.count = (long long)cnt;
+    a->result.nfields = nf;
+    for (int j = 0; j < 32; ++j) a->result.cols[j] = nullptr;
+    if (a->flags & SDQLB200_F_NOFETCH) return SDQLB200_OK;
+    for (int j = 0; j < nf; ++j) {
+        a->result.cols[j] = (int64_t*)malloc((cnt ? cnt : 1) * 8);
+        if (cnt) SDQL_CUDA(cudaMemcpyAsync(a->result.cols[j], d_cols[j], cnt * 8, cudaMemcpyDeviceToHost, st));
+    }
+    SDQL_CUDA(cudaStreamSynchronize(st));
+    return SDQLB200_OK;
+}
+
+'''
+
+MODULE_TAIL = r'''
+struct sdql_entry { const char* name; int (*fn)(sdqlb200_args*); };
+static const sdql_entry g_queries[] = {
+%(entries)s
+};
+static const char g_manifest[] = %(manifest)s;
+
+extern "C" {
+int sdqlb200_num_queries(void) { return (int)(sizeof g_queries / sizeof g_queries[0]); }
+const char* sdqlb200_query_name(int i) { return (i >= 0 && i < sdqlb200_num_queries()) ? g_queries[i].name : nullptr; }
+const char* sdqlb200_manifest(void) { return g_manifest; }
+const char* sdqlb200_last_error(void) { return sdqlhost::g_err; }
+int sdqlb200_run(const char* query, sdqlb200_args* args) {
+    if (!query || !args) return sdqlhost::fail(SDQLB200_E_ARG, "null argument");
+    for (int i = 0; i < sdqlb200_num_queries(); ++i)
+        if (!strcmp(g_queries[i].name, query)) return g_queries[i].fn(args);
+    return sdqlhost::fail(SDQLB200_E_NOQUERY, "no query named %%s in this module", query);
+}
+void sdqlb200_result_free(sdqlb200_result* r) {
+    if (!r) return;
+    for (int j = 0; j < 32; ++j) { free(r->cols[j]); r->cols[j] = nullptr; }
+    r->count = 0;
+}
+}
+'''
+
+
+def render_module(queries, src_name):
+    body = [MODULE_HEAD % {"src": src_name}]
+    for q in queries:
+        body.append(render_query(q))
+    man = json.dumps({"queries": [manifest_of(q) for q in queries]})
+    lit = "\n".join("    " + cstr(man[i:i + 100]) for i in range(0, len(man), 100))
+    entries = "\n".join('    {"%s", %s_run},' % (q.name, q.name) for q in queries)
+    body.append(MODULE_TAIL % {"entries": entries, "manifest": "\n" + lit})
+    return "\n".join(body)
+
+
+def schema_from_in_type(in_type_node_or_obj):
+    raise NotImplementedError

@@ -1,0 +1,257 @@
+// sdqlpy-b200 device runtime: the hand-written sm_100a building blocks that generated query kernels are
+// assembled from (replaces the reference's native runtime L5: varchar.h, tuple_helper.h, map_helper.h and the
+// vendored phmap -- SURVEY.md section 2 rows 11/12).
+//
+//   * streaming column loads    128-bit / 256-bit ld.global.nc.L1::no_allocate, 4 rows per thread per column
+//   * Tbl                       one device dictionary: direct-indexed (dense key domain) or open-addressing hash
+//                               (atomicCAS claim, linear probing); every slot keeps a representative source index
+//   * reductions                warp-shuffle + shared-memory block reductions (fp64 / int64)
+//   * fixed-width byte strings  ==, startsWith, endsWith, firstIndex/contains with the reference's VarChar
+//                               semantics (varchar.h:61-135) but bounded to the row (no over-read)
+//
+// SDQLB200_EMU: compile the same code as plain single-threaded C++ (tests/ only: lets the GPU-less dev container
+// check generated query logic; never built into or loaded by the package).
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#ifndef SDQLB200_EMU
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#define SDQL_DEV __device__ __forceinline__
+#define SDQL_EXTERN_SMEM(name) extern __shared__ unsigned long long name[]
+#define SDQL_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#else
+#include "sdqlb200_emu.h"
+#define SDQL_DEV static inline
+#endif
+
+namespace sdqlrt {
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+constexpr int kBlock = 256;   // threads per CTA for every generated kernel
+constexpr int kVec = 4;       // rows per thread per iteration
+constexpr u64 kEmpty = ~0ull;
+
+// ---------------------------------------------------------------------------------------------
+// streaming loads
+// ---------------------------------------------------------------------------------------------
+#ifndef SDQLB200_EMU
+SDQL_DEV void ld4(const int* p, int (&v)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p));
+}
+SDQL_DEV void ld4(const double* p, double (&v)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "l"(p + 2));
+}
+SDQL_DEV void ld4(const unsigned char* p, int (&v)[4]) {
+    unsigned w;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(w) : "l"(p));
+    v[0] = w & 0xff; v[1] = (w >> 8) & 0xff; v[2] = (w >> 16) & 0xff; v[3] = w >> 24;
+}
+template <class T> SDQL_DEV T ld1(const T* p) { return __ldg(p); }
+#else
+template <class T, class V> SDQL_DEV void ld4(const T* p, V (&v)[4]) { for (int k = 0; k < 4; ++k) v[k] = (V)p[k]; }
+template <class T> SDQL_DEV T ld1(const T* p) { return *p; }
+#endif
+
+// dictionary-code columns are uint8 when the dictionary has <= 256 entries, int32 otherwise (uniform branch)
+SDQL_DEV void ld4_code(const void* p, i64 i0, int width, int (&v)[4]) {
+    if (width == 1) ld4((const unsigned char*)p + i0, v);
+    else ld4((const int*)p + i0, v);
+}
+SDQL_DEV int ld1_code(const void* p, i64 i, int width) {
+    return width == 1 ? (int)ld1((const unsigned char*)p + i) : ld1((const int*)p + i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// device dictionary
+// ---------------------------------------------------------------------------------------------
+struct Tbl {
+    u64* keys;   // hash mode: packed key per slot (kEmpty = free); unused in direct mode
+    int* rep;    // representative source index (row of the scanned relation / slot of the scanned table); -1 = free
+    i64 cap;     // slots (direct: key domain size; hash: power of two)
+    int direct;  // 1: slot == packed key
+};
+
+SDQL_DEV u64 hash64(u64 x) {  // splitmix64 finaliser
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+    return x;
+}
+
+// -> slot or -1.  `ok` = every key part was inside the table's packing range.
+SDQL_DEV int tbl_find(const Tbl& t, u64 key, bool ok) {
+    if (!ok) return -1;
+    if (t.direct) return ld1(t.rep + key) >= 0 ? (int)key : -1;
+    u64 m = (u64)t.cap - 1, h = hash64(key) & m;
+    for (;;) {
+        u64 k = ld1(t.keys + h);
+        if (k == key) return (int)h;
+        if (k == kEmpty) return -1;
+        h = (h + 1) & m;
+    }
+}
+
+// insert-or-find; `src` becomes the slot's representative if the slot is new.  -> slot
+SDQL_DEV int tbl_upsert(const Tbl& t, u64 key, int src, bool& is_new) {
+    if (t.direct) {
+        int old = t.rep[key];
+        if (old < 0) old = atomicCAS(t.rep + key, -1, src);
+        is_new = old < 0;
+        return (int)key;
+    }
+    u64 m = (u64)t.cap - 1, h = hash64(key) & m;
+    for (;;) {
+        u64 k = t.keys[h];
+        if (k == key) { is_new = false; return (int)h; }
+        if (k == kEmpty) {
+            u64 prev = atomicCAS(t.keys + h, kEmpty, key);
+            if (prev == kEmpty) { t.rep[h] = src; is_new = true; return (int)h; }
+            if (prev == key) { is_new = false; return (int)h; }
+        }
+        h = (h + 1) & m;
+    }
+}
+
+SDQL_DEV int rep_of(const Tbl& t, int slot) {  // safe for slot == -1 (returns a valid index >= 0)
+    int r = ld1(t.rep + (slot < 0 ? 0 : slot));
+    return r < 0 ? 0 : r;
+}
+
+// mixed-radix key packing: part p in [mn, mn + rng) contributes (p - mn) * mul
+SDQL_DEV bool pack_part(i64 p, i64 mn, i64 rng, i64 mul, u64& key) {
+    u64 d = (u64)(p - mn);
+    key += d * (u64)mul;
+    return d < (u64)rng;
+}
+
+SDQL_DEV i64 unpack_part(u64 key, i64 mn, i64 rng, i64 mul) {
+    if (rng < 0) return (i64)key;  // single unbounded part
+    return (i64)((key / (u64)mul) % (u64)rng) + mn;
+}
+SDQL_DEV u64 tbl_key(const Tbl& t, i64 slot) { return t.direct ? (u64)slot : ld1(t.keys + slot); }
+
+// ---------------------------------------------------------------------------------------------
+// atomics / reductions
+// ---------------------------------------------------------------------------------------------
+SDQL_DEV void red_add(double* p, double v) { atomicAdd(p, v); }
+SDQL_DEV void red_add(i64* p, i64 v) { atomicAdd((u64*)p, (u64)v); }
+
+#ifndef SDQLB200_EMU
+template <class T> SDQL_DEV T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+SDQL_DEV int warp_max(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// all threads must call; result valid in thread 0.  Sum order is fixed (lane tree, then warp 0 tree) so the
+// result is run-to-run deterministic for a fixed grid.
+template <class T> SDQL_DEV T block_sum(T v) {
+    __shared__ T sh[kBlock / 32];
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T r = 0;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : (T)0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+SDQL_DEV int block_max(int v) {
+    __shared__ int shm[kBlock / 32];
+    v = warp_max(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) shm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = -1;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < (blockDim.x >> 5) ? shm[threadIdx.x] : -1;
+        r = warp_max(r);
+    }
+    return r;
+}
+// warp-aggregated append: one atomicAdd per converged group of appending lanes
+SDQL_DEV u64 append_slot(u64* counter) {
+    auto g = cooperative_groups::coalesced_threads();
+    u64 base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(counter, (u64)g.size());
+    return g.shfl(base, 0) + g.thread_rank();
+}
+#else
+template <class T> SDQL_DEV T block_sum(T v) { return v; }
+SDQL_DEV int block_max(int v) { return v; }
+SDQL_DEV u64 append_slot(u64* counter) { return (*counter)++; }
+#endif
+
+// "last block done" election for two-level reductions; `counter` must be zero before the launch and is reset.
+SDQL_DEV bool last_block(unsigned* counter) {
+#ifndef SDQLB200_EMU
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(counter, 1u);
+        last = (t == gridDim.x - 1);
+        if (last) *counter = 0;
+    }
+    __syncthreads();
+    if (last) __threadfence();
+    return last;
+#else
+    return true;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// fixed-width, zero-padded byte strings (device form of VarChar<N>, 1 byte per char)
+// ---------------------------------------------------------------------------------------------
+SDQL_DEV int str_len(const unsigned char* s, int w) {
+    int n = 0;
+    while (n < w && s[n]) ++n;
+    return n;
+}
+// first index of pat in s, -1 if absent (varchar.h:91-97 firstIndex -> wcsstr, which stops at the first NUL)
+SDQL_DEV int str_find(const unsigned char* s, int w, const char* pat, int plen) {
+    int n = str_len(s, w);
+    for (int i = 0; i + plen <= n; ++i) {
+        int j = 0;
+        while (j < plen && s[i + j] == (unsigned char)pat[j]) ++j;
+        if (j == plen) return i;
+    }
+    return -1;
+}
+SDQL_DEV bool str_starts(const unsigned char* s, int w, const char* pat, int plen) {  // varchar.h:99-111
+    if (plen > w) return false;
+    for (int j = 0; j < plen; ++j)
+        if (s[j] != (unsigned char)pat[j]) return false;
+    return true;
+}
+// varchar.h:113-125: endsWith == (firstIndex(pat) == len - plen), i.e. the FIRST occurrence must be the suffix
+SDQL_DEV bool str_ends(const unsigned char* s, int w, const char* pat, int plen) {
+    return str_find(s, w, pat, plen) == str_len(s, w) - plen;
+}
+SDQL_DEV bool str_eq(const unsigned char* s, int w, const char* pat, int plen) {  // varchar.h:61-77
+    if (plen > w) return false;
+    for (int j = 0; j < plen; ++j)
+        if (s[j] != (unsigned char)pat[j]) return false;
+    for (int j = plen; j < w; ++j)
+        if (s[j]) return false;
+    return true;
+}
+SDQL_DEV i64 str_pack(const unsigned char* s, int from, int n) {  // substr<n>(from, from+n-1) as an integer key
+    u64 v = 0;
+    for (int j = 0; j < n; ++j) v = (v << 8) | s[from + j];
+    return (i64)v;
+}
+
+}  // namespace sdqlrt

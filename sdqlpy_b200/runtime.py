@@ -1,0 +1,388 @@
+"""Host runtime: loads a generated query module through the C ABI of include/sdqlb200.h (ctypes), keeps the
+device-resident columnar store, resolves constants, owns the device workspace and boxes results.
+
+This is the reference-facing side of the boundary:
+  * ``load_compiled(script)`` returns a module-like object with ``<fn>_compiled(db)`` callables -- the names the
+    reference dispatcher looks up (sdql_lib.py:401-410), ``db`` being the same list-of-lists of columns
+    (sdql_lib.py:420-424; row count and column pointers as in sdql_compiler.py:644-668).
+  * results: float / int, or a ``ResultSet`` with the ``fastd`` API (size / print / to_dict, fastd.py:31-51).
+
+PyTorch is used for device memory and streams only.  There is no CPU fallback: without a CUDA device (or
+without the built module) every entry point raises.
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+
+from . import build
+
+KIND_ID = {"i32": 0, "f64": 1, "code": 2, "bytes": 3}
+E_WORKSPACE = -1
+F_NOFETCH = 1
+
+
+class Col(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("rows", ctypes.c_int64), ("min", ctypes.c_int64), ("max", ctypes.c_int64),
+                ("width", ctypes.c_int32), ("kind", ctypes.c_int32)]
+
+
+class Result(ctypes.Structure):
+    _fields_ = [("count", ctypes.c_int64), ("nfields", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("cols", ctypes.POINTER(ctypes.c_int64) * 32)]
+
+
+class Args(ctypes.Structure):
+    _fields_ = [("cols", ctypes.POINTER(Col)), ("ncols", ctypes.c_int32), ("nargs", ctypes.c_int32),
+                ("nrows", ctypes.POINTER(ctypes.c_int64)), ("consts", ctypes.POINTER(ctypes.c_int64)),
+                ("nconsts", ctypes.c_int32), ("flags", ctypes.c_int32), ("workspace", ctypes.c_void_p),
+                ("workspace_bytes", ctypes.c_uint64), ("workspace_needed", ctypes.c_uint64),
+                ("stream", ctypes.c_void_p), ("device_ms", ctypes.c_float), ("launches", ctypes.c_int32),
+                ("tier", ctypes.c_int32), ("reserved", ctypes.c_int32), ("result", Result)]
+
+
+# ---------------------------------------------------------------------------------------------
+# device memory back end
+# ---------------------------------------------------------------------------------------------
+class CudaBackend:
+    """device buffers = torch tensors on the current CUDA device."""
+    name = "cuda"
+
+    def __init__(self):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("sdqlpy_b200: no CUDA device -- the B200 backend has no CPU fallback")
+        self.torch = torch
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+
+    def upload(self, arr):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr))
+        d = t.to(self.dev, non_blocking=False)
+        return d.data_ptr(), d
+
+    def alloc(self, nbytes):
+        d = self.torch.empty(max(int(nbytes), 256), dtype=self.torch.uint8, device=self.dev)
+        return d.data_ptr(), d
+
+    def stream(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+
+
+_backend = None
+
+
+def backend():
+    global _backend
+    if _backend is None:
+        _backend = CudaBackend()
+    return _backend
+
+
+def set_backend(b):
+    global _backend
+    _backend = b
+
+
+# ---------------------------------------------------------------------------------------------
+# columnar store
+# ---------------------------------------------------------------------------------------------
+class DeviceColumn:
+    __slots__ = ("kind", "ptr", "holder", "rows", "min", "max", "width", "dictionary", "nbytes")
+
+    def __init__(self, kind, ptr, holder, rows, mn, mx, width, dictionary=None, nbytes=0):
+        self.kind, self.ptr, self.holder, self.rows = kind, ptr, holder, rows
+        self.min, self.max, self.width, self.dictionary, self.nbytes = mn, mx, width, dictionary, nbytes
+
+
+def _ustr_to_bytes(a, width):
+    n = a.dtype.itemsize // 4
+    m = np.ascontiguousarray(a).view(np.uint32).reshape(len(a), n)
+    if (m > 255).any():
+        raise ValueError("non-latin1 characters are not supported in string columns")
+    out = np.zeros((len(a), width), dtype=np.uint8)
+    out[:, :min(n, width)] = m[:, :width]
+    return out
+
+
+def _encode(src, rep, width):
+    """host column (numpy array or tpch.gen.Column) -> (numpy device image, min, max, elem width, dictionary)."""
+    from .tpch.gen import Column
+    if isinstance(src, Column):
+        if rep == "i32":
+            a = src.data.astype(np.int32, copy=False)
+            return a, int(a.min()) if len(a) else 0, int(a.max()) if len(a) else 0, 4, None
+        if rep == "f64":
+            return src.data.astype(np.float64, copy=False), 0, 0, 8, None
+        if rep == "code":
+            if src.kind == "code":
+                a = src.data if len(src.dictionary) <= 256 else src.data.astype(np.int32)
+                return a, 0, len(src.dictionary) - 1, a.dtype.itemsize, list(src.dictionary)
+            if src.kind == "bytes":
+                v = np.ascontiguousarray(src.data).view(np.dtype((np.void, src.data.shape[1]))).reshape(-1)
+                u, inv = np.unique(v, return_inverse=True)
+                d = [bytes(x).rstrip(b"\0").decode("latin1") for x in u]
+                a = inv.astype(np.uint8 if len(d) <= 256 else np.int32)
+                return a, 0, len(d) - 1, a.dtype.itemsize, d
+        if rep == "bytes":
+            if src.kind == "bytes":
+                m = src.data
+                if m.shape[1] != width:
+                    mm = np.zeros((m.shape[0], width), dtype=np.uint8)
+                    mm[:, :min(width, m.shape[1])] = m[:, :width]
+                    m = mm
+                return m, 0, 0, width, None
+            if src.kind == "code":
+                tab = np.zeros((len(src.dictionary), width), dtype=np.uint8)
+                for i, s in enumerate(src.dictionary):
+                    b = s.encode("latin1")[:width]
+                    tab[i, :len(b)] = np.frombuffer(b, dtype=np.uint8)
+                return tab[src.data], 0, 0, width, None
+        raise ValueError("cannot provide column %s as %s" % (src.name, rep))
+    a = np.asarray(src)
+    if rep == "i32":
+        if a.dtype.kind not in "iu":
+            raise ValueError("integer column expected, got %s" % a.dtype)
+        mn, mx = (int(a.min()), int(a.max())) if len(a) else (0, 0)
+        if mn < -2**31 or mx >= 2**31:
+            raise ValueError("integer column outside int32 range (device layout is int32 in this version)")
+        return a.astype(np.int32), mn, mx, 4, None
+    if rep == "f64":
+        return a.astype(np.float64, copy=False), 0, 0, 8, None
+    if a.dtype.kind != "U":
+        raise ValueError("string column expected, got %s" % a.dtype)
+    if rep == "code":
+        u, inv = np.unique(a, return_inverse=True)
+        d = [str(x) for x in u]
+        c = inv.astype(np.uint8 if len(d) <= 256 else np.int32)
+        return c, 0, len(d) - 1, c.dtype.itemsize, d
+    if rep == "bytes":
+        return _ustr_to_bytes(a, width), 0, 0, width, None
+    raise ValueError(rep)
+
+
+class ColumnStore:
+    """device copies keyed by (identity of the host column, representation) -- repeated calls with the same host
+    arrays (the reference's benchmark() loop, sdql_lib.py:445-452) do not re-upload."""
+
+    def __init__(self):
+        self.cache = {}
+        self.enabled = True
+        self.h2d_bytes = 0
+
+    def key(self, src):
+        if isinstance(src, np.ndarray):
+            return ("np", src.__array_interface__["data"][0], src.nbytes, str(src.dtype))
+        return ("obj", id(src))
+
+    def get(self, src, rep, width):
+        if isinstance(src, DeviceColumn):
+            if src.kind != rep:
+                raise ValueError("device column is '%s', query needs '%s'" % (src.kind, rep))
+            return src
+        k = (self.key(src), rep, width)
+        if self.enabled and k in self.cache:
+            return self.cache[k][0]
+        img, mn, mx, w, d = _encode(src, rep, width)
+        ptr, holder = backend().upload(img)
+        self.h2d_bytes += img.nbytes
+        col = DeviceColumn(rep, ptr, holder, img.shape[0], mn, mx, w, d, img.nbytes)
+        if self.enabled:
+            self.cache[k] = (col, src)  # keep the host object alive so the identity key stays valid
+        return col
+
+    def clear(self):
+        self.cache.clear()
+
+
+STORE = ColumnStore()
+
+
+def host_strings(src, rows):
+    """values of a host string column at the given row ids (late materialisation of string result fields)."""
+    from .tpch.gen import Column
+    rows = np.asarray(rows, dtype=np.int64)
+    if isinstance(src, Column):
+        if src.kind == "code":
+            return [src.dictionary[c] for c in src.data[rows]]
+        return [bytes(r).split(b"\0", 1)[0].decode("latin1") for r in src.data[rows]]
+    if isinstance(src, DeviceColumn):
+        raise ValueError("string result fields need the host copy of the column")
+    return [str(x) for x in np.asarray(src)[rows]]
+
+
+# ---------------------------------------------------------------------------------------------
+# results (fastd-compatible surface)
+# ---------------------------------------------------------------------------------------------
+class ResultSet:
+    """set of records returned by a query: the surface of the reference's fastd wrapper (fastd.py:31-51)."""
+
+    def __init__(self, names, rows):
+        self.names, self.rows = list(names), rows
+
+    def size(self):
+        return len(self.rows)
+
+    def __len__(self):
+        return len(self.rows)
+
+    def to_dict(self):
+        from .sdql_lib import record, sr_dict
+        return sr_dict({record(dict(zip(self.names, r))): True for r in self.rows})
+
+    def tuples(self):
+        return list(self.rows)
+
+    def __str__(self):  # 2-decimal printing like the reference (phmap.h:83)
+        def f(v):
+            return "%.2f" % v if isinstance(v, float) else str(v)
+        return "{" + ", ".join("<" + ",".join(f(v) for v in r) + ">:true" for r in self.rows) + "}"
+
+    def print(self):
+        print(str(self))
+
+
+# ---------------------------------------------------------------------------------------------
+# module
+# ---------------------------------------------------------------------------------------------
+class RunInfo:
+    __slots__ = ("device_ms", "launches", "tier", "workspace_bytes", "h2d_bytes", "d2h_bytes", "rows")
+
+
+class CompiledModule:
+    def __init__(self, so_path):
+        if not os.path.exists(so_path):
+            raise ImportError("compiled query module %s not found (run sdqlpy_init(1, ..) / build())" % so_path)
+        self.path = so_path
+        self.lib = ctypes.CDLL(so_path)
+        self.lib.sdqlb200_manifest.restype = ctypes.c_char_p
+        self.lib.sdqlb200_last_error.restype = ctypes.c_char_p
+        self.lib.sdqlb200_run.argtypes = [ctypes.c_char_p, ctypes.POINTER(Args)]
+        self.lib.sdqlb200_result_free.argtypes = [ctypes.POINTER(Result)]
+        man = json.loads(self.lib.sdqlb200_manifest().decode())
+        self.queries = {q["name"]: q for q in man["queries"]}
+        self.ws = None
+        self.ws_bytes = 0
+        self.last = None
+        for name in self.queries:
+            setattr(self, name + "_compiled", self._make(name))
+
+    def _make(self, name):
+        def call(db):
+            return self.run(name, db)
+        call.__name__ = name + "_compiled"
+        return call
+
+    def prepare(self, name, db):
+        """resolve device inputs + constants for a query; -> (Args, keepalive)"""
+        q = self.queries[name]
+        argpos = {a: i for i, a in enumerate(q["args"])}
+        if len(db) != len(q["args"]):
+            raise ValueError("%s expects %d relations, got %d" % (name, len(q["args"]), len(db)))
+        cols = []
+        for arg, col, rep in q["inputs"]:
+            names = [c for c, _ in q["schemas"][arg]]
+            kind = dict((c, k) for c, k in q["schemas"][arg])[col]
+            width = kind[1] if isinstance(kind, list) else 0
+            cols.append(STORE.get(db[argpos[arg]][names.index(col)], rep, width))
+        nrows = []
+        for a in q["args"]:
+            first = db[argpos[a]][0]
+            nrows.append(first.rows if isinstance(first, DeviceColumn) else
+                         (first.data.shape[0] if hasattr(first, "kind") else len(first)))
+        consts = []
+        for kind, arg, col, lit in q["consts"]:
+            idx = [i for i, k in enumerate(q["inputs"]) if k == [arg, col, "code"]]
+            d = cols[idx[0]].dictionary
+            consts.append(d.index(lit) if lit in d else -1)
+        a = Args()
+        carr = (Col * max(1, len(cols)))()
+        for i, c in enumerate(cols):
+            carr[i] = Col(c.ptr, c.rows, c.min, c.max, c.width, KIND_ID[c.kind])
+        narr = (ctypes.c_int64 * max(1, len(nrows)))(*nrows)
+        karr = (ctypes.c_int64 * max(1, len(consts)))(*consts)
+        a.cols, a.ncols, a.nargs, a.nrows = carr, len(cols), len(nrows), narr
+        a.consts, a.nconsts = karr, len(consts)
+        return a, (cols, carr, narr, karr)
+
+    def execute(self, name, a, fetch=True):
+        be = backend()
+        a.flags = 0 if fetch else F_NOFETCH
+        a.stream = be.stream()
+        a.workspace, a.workspace_bytes = (self.ws[0] if self.ws else None), self.ws_bytes
+        rc = self.lib.sdqlb200_run(name.encode(), ctypes.byref(a))
+        if rc == E_WORKSPACE:
+            need = int(a.workspace_needed)
+            self.ws = None
+            self.ws = be.alloc(need + (need >> 3))
+            self.ws_bytes = need + (need >> 3)
+            a.workspace, a.workspace_bytes = self.ws[0], self.ws_bytes
+            rc = self.lib.sdqlb200_run(name.encode(), ctypes.byref(a))
+        if rc != 0:
+            raise RuntimeError("sdqlb200_run(%s) failed (%d): %s" % (name, rc, self.lib.sdqlb200_last_error().decode()))
+        return a
+
+    def run(self, name, db):
+        h2d0 = STORE.h2d_bytes
+        a, keep = self.prepare(name, db)
+        self.execute(name, a)
+        q = self.queries[name]
+        res = a.result
+        n, nf = int(res.count), int(res.nfields)
+        cols = [np.ctypeslib.as_array(res.cols[j], shape=(max(n, 1),))[:n].copy() for j in range(nf)]
+        self.lib.sdqlb200_result_free(ctypes.byref(a.result))
+        info = RunInfo()
+        info.device_ms, info.launches, info.tier = float(a.device_ms), int(a.launches), int(a.tier)
+        info.workspace_bytes, info.h2d_bytes, info.d2h_bytes, info.rows = int(a.workspace_needed), STORE.h2d_bytes - h2d0, 8 + n * nf * 8, n
+        self.last = info
+        return self.box(q, db, cols, n)
+
+    def box(self, q, db, cols, n):
+        kind = q["result_kind"]
+        if kind == "f64":
+            return float(cols[0].view(np.float64)[0])
+        if kind == "i64":
+            return int(cols[0][0])
+        argpos = {a: i for i, a in enumerate(q["args"])}
+        out, names = [], []
+        for (fname, fk), c in zip(q["result"], cols):
+            names.append(fname)
+            if fk == "f64":
+                out.append(c.view(np.float64).tolist())
+            elif fk == "i64":
+                out.append(c.tolist())
+            elif fk == "bool":
+                out.append([bool(x) for x in c])
+            elif fk.startswith("str:ref:"):
+                _, _, arg, col = fk.split(":")
+                cn = [x for x, _ in q["schemas"][arg]]
+                out.append(host_strings(db[argpos[arg]][cn.index(col)], c))
+            elif fk.startswith("str:code:"):
+                _, _, arg, col = fk.split(":")
+                cn = [x for x, _ in q["schemas"][arg]]
+                kindc = dict((x, k) for x, k in q["schemas"][arg])[col]
+                d = STORE.get(db[argpos[arg]][cn.index(col)], "code", kindc[1]).dictionary
+                out.append([d[i] for i in c])
+            elif fk.startswith("str:pack:"):
+                nb = int(fk.split(":")[2])
+                out.append([int(v).to_bytes(nb, "big").split(b"\0", 1)[0].decode("latin1") for v in c])
+            elif fk.startswith("str:const:"):
+                out.append([fk[len("str:const:"):]] * n)
+            else:
+                raise ValueError(fk)
+        rows = list(dict.fromkeys(zip(*out))) if out and n else []
+        return ResultSet(names, rows)
+
+
+_modules = {}
+
+
+def load_compiled(script_path):
+    """the module object the dispatcher imports as <script>_compiled (sdql_lib.py:401-402)."""
+    _, so = build.out_paths(script_path)
+    if so not in _modules:
+        _modules[so] = CompiledModule(so)
+    return _modules[so]
