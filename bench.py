@@ -1,0 +1,312 @@
+#!/usr/bin/env python3
+"""Headline benchmark: TPC-H Q1 at SF10 per GPU (BASELINE.json configs[1]) -- scan GB/s and per-query latency.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--query q1] [--sf 10]
+
+One "step" = one execution of the query over one batch of synthetic lineitem rows.
+  value   : whole-job scan throughput, algorithmic bytes of the DEVICE layout / CUDA-event time, inputs resident in HBM
+  e2e     : the same metric through the reference-facing call <fn>_compiled(db) with HOST (pinned) columns: every step
+            re-uploads the query's input columns, runs, and reads the result back
+  roofline: dominant kernel, bytes per launch / its own CUDA-event time, against MEASURED_PEAKS.json
+  N > 1   : weak scaling -- rank r owns the r-th order range of an SF*N database (lineitem range partitioned on order
+            boundaries, as north_star), partial results are exchanged with one NCCL all-gather per step and merged.
+--impl reference times the reference's own generated C++ (oracle/_ref, TBB-shim threads = host cores) on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from sdqlpy_b200.tpch.gen import SCHEMAS, TPCH  # noqa: E402
+
+QUERY_SCRIPT = os.path.join(ROOT, "sdqlpy_b200", "tpch", "queries.py")
+ELEM_BYTES = {"i32": 4, "f64": 8}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        self.lines, self.proc, self.gpu = [], None, gpu
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def scan_bytes_per_row(man, relation_arg):
+    """algorithmic bytes one scanned row of ``relation_arg`` costs in the device layout."""
+    total, cols = 0, []
+    for k in man["kernels"]:
+        if k["source"] == ["rel", relation_arg]:
+            for c, rep in k["scan_cols"]:
+                b = ELEM_BYTES.get(rep, 1)
+                total += b
+                cols.append("%s:%d" % (c, b))
+    return total, cols
+
+
+def lineitem_columns(g, man, order_range):
+    need = sorted({c for a, c, r in man["inputs"] if a == "li"})
+    return g.columns("lineitem", need, order_range)
+
+
+def ref_arm(args, nproc):
+    """the reference's own CPU implementation of the path, all host threads, on a bounded sample."""
+    import ref_runner as rr
+    os.environ["SDQL_REF_THREADS"] = str(nproc)
+    name = "tpchref_sf10_t8" if rr.available("tpchref_sf10_t8") else "tpchref_sf1_t8"
+    mod = rr.load(name)
+    sample_sf = min(args.sf, args.ref_sample_sf)
+    g = TPCH(sample_sf)
+    q = args.query
+    db = []
+    man = json.load(open(os.path.join(ROOT, "sdqlpy_b200", "tpch", "sdqlb200_generated", "manifest.json")))
+    qm = [x for x in man["queries"] if x["name"] == q][0]
+    for a, t in zip(qm["args"], rr.QUERY_ARGS[q]):
+        db.append(g.ref_table(t, [c for aa, c, r in qm["inputs"] if aa == a]))
+    rows = len(db[qm["args"].index("li")][0]) if "li" in qm["args"] else 0
+    bpr, _ = scan_bytes_per_row(qm, "li")
+    fn = getattr(mod, q + "_compiled")
+    for _ in range(args.warmup):
+        fn(db)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn(db)
+    dt = (time.perf_counter() - t0) / args.steps
+    gbs = rows * bpr / dt / 1e9
+    sample = "lineitem of TPC-H SF%g (%d rows, reference layout int64/fp64/UCS4), %s, %d TBB-shim threads" % (
+        sample_sf, rows, name, nproc)
+    return gbs, dt * 1e3, rows, sample
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--query", default="q1")
+    ap.add_argument("--sf", type=float, default=10.0)
+    ap.add_argument("--ref-sample-sf", type=float, default=2.0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    nproc = os.cpu_count() or 1
+    q = args.query
+    workload = "tpch_%s_sf%g_per_gpu" % (q, args.sf)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        gbs, ms, rows, sample = ref_arm(args, nproc)
+        print(json.dumps({
+            "impl": "reference", "metric": "tpch_%s_scan_throughput" % q, "value": gbs, "unit": "GB/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "rows_per_step": rows,
+                       "bytes_per_row": "device-layout bytes (same numerator as the b200 arm)"},
+            "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": nproc, "kind": "reference", "sample": sample},
+            "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from sdqlpy_b200 import runtime
+    mod = runtime.load_compiled(QUERY_SCRIPT)
+    man = mod.queries[q]
+    if man["args"] != ["li"]:
+        raise SystemExit("bench.py drives single-relation lineitem scans (q1, q6); use tools/run_tpch.py for the others")
+    # ---- data: rank r owns the r-th order range of an SF*world database -------------------------------------
+    g = TPCH(args.sf * world)
+    o_per = g.O // world
+    orng = (rank * o_per, (rank + 1) * o_per if rank < world - 1 else g.O)
+    cols = lineitem_columns(g, man, orng)
+    names = [c for c, _ in SCHEMAS["lineitem"]]
+    be = runtime.backend()
+    pinned, keep = {}, []
+    for c, col in cols.items():  # host copies live in page-locked memory (source of the e2e uploads)
+        v, t = be.pinned_like(col.data)
+        col.data = v
+        keep.append(t)
+    db = [[cols.get(c) for c in names]]
+    rows = len(next(iter(cols.values())).data)
+    bpr, bcols = scan_bytes_per_row(man, "li")
+    step_bytes = rows * bpr
+    # ---- device-resident timing ---------------------------------------------------------------------------
+    a, keepalive = mod.prepare(q, db)
+    torch.cuda.synchronize()
+
+    def merge(res_rows):
+        """N > 1: exchange partial result rows (one NCCL all-gather), merge by key on every rank."""
+        if world == 1:
+            return res_rows
+        buf = torch.zeros(64, 8, dtype=torch.int64, device="cuda")
+        n = min(len(res_rows), 64)
+        if n:
+            buf[:n, :len(res_rows[0])] = torch.tensor(res_rows[:n], dtype=torch.int64)
+        out = torch.empty(world * 64, 8, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(out, buf)
+        return out
+
+    def step():
+        mod.execute(q, a, fetch=True)
+        res = a.result
+        n, nf = int(res.count), int(res.nfields)
+        rows_ = [[int(res.cols[j][i]) for j in range(nf)] for i in range(min(n, 64))]
+        mod.lib.sdqlb200_result_free(__import__("ctypes").byref(a.result))
+        merge(rows_)
+        return float(a.device_ms), int(a.launches)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev_ms, launches = [], 0
+    e0.record()
+    for _ in range(args.steps):
+        ms, ln = step()
+        dev_ms.append(ms)
+        launches += ln
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = e0.elapsed_time(e1)
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    rows_t = torch.tensor([rows], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(rows_t)
+    all_bytes = float(rows_t.item()) * bpr
+    value = all_bytes / (ms_per_step * 1e-3) / 1e9
+    # ---- roofline of the dominant kernel (its own CUDA events) ---------------------------------------------
+    kms = []
+    for _ in range(5):
+        mod.execute(q, a, fetch=True, kernel_times=True)
+        mod.lib.sdqlb200_result_free(__import__("ctypes").byref(a.result))
+        kms.append([a.kernel_ms[k] for k in range(int(a.launches))])
+    kavg = np.mean(np.array(kms), axis=0)
+    dom = int(np.argmax(kavg))
+    peak, peak_src = peaks()
+    achieved = step_bytes / (kavg[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": man["kernels"][dom]["name"], "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": float(kavg[dom]), "bytes_per_launch": step_bytes,
+                "kernel_share_of_step": float(kavg[dom] / max(1e-9, np.mean(dev_ms)))}
+    prof = os.path.join(ROOT, "profiles", "r01_%s_traffic.json" % q)
+    if os.path.exists(prof):
+        roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+    # ---- end to end through <fn>_compiled(db): host columns, upload every step -------------------------------
+    runtime.STORE.enabled = False
+    runtime.STORE.clear()
+    fn = getattr(mod, q + "_compiled")
+    fn(db)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        r = fn(db)
+        merge([[0]])
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e = {"value": all_bytes / e2e_s / 1e9, "unit": "GB/s", "ms_per_step": e2e_s * 1e3,
+           "h2d_bytes_per_step": int(mod.last.h2d_bytes), "d2h_bytes_per_step": int(mod.last.d2h_bytes),
+           "note": "host columns in pinned memory, compact device layout; %d steps" % args.e2e_steps}
+    runtime.STORE.enabled = True
+    out = {
+        "metric": "tpch_%s_scan_throughput" % q, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "query": q, "sf_per_gpu": args.sf, "rows_per_gpu": rows,
+                   "bytes_per_row": bpr, "layout": bcols, "l2_policy": "inputs (%.2f GB per GPU) larger than L2" % (step_bytes / 1e9),
+                   "latency_ms_device": float(np.mean(dev_ms)), "agg_tier": int(a.tier)},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            a2 = argparse.Namespace(**vars(args))
+            a2.steps, a2.warmup = 5, 1
+            gbs, ms, rrows, sample = ref_arm(a2, nproc)
+            out["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "cores": nproc, "kind": "reference", "sample": sample,
+                                   "ms_per_step": ms}
+        except Exception as ex:  # the checker is missing: say so, do not fake a number
+            out["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": nproc, "kind": "reference",
+                                   "sample": "unavailable: %r" % (ex,)}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -20,7 +20,7 @@ extern "C" {
 
 enum { SDQLB200_I32 = 0, SDQLB200_F64 = 1, SDQLB200_CODE = 2, SDQLB200_BYTES = 3 };
 enum { SDQLB200_OK = 0, SDQLB200_E_WORKSPACE = -1, SDQLB200_E_CUDA = -2, SDQLB200_E_ARG = -3, SDQLB200_E_NOQUERY = -4 };
-enum { SDQLB200_F_NOFETCH = 1 };
+enum { SDQLB200_F_NOFETCH = 1, SDQLB200_F_KERNEL_TIMES = 2 };
 
 /* one device-resident column (replaces the borrowed numpy buffer of sdql_compiler.py:653-668) */
 typedef struct {
@@ -56,6 +56,7 @@ typedef struct {
     int32_t tier;             /* out: aggregation tier of the last group-by kernel (0/1/2)      */
     int32_t reserved;
     sdqlb200_result result;   /* out                                                            */
+    float kernel_ms[24];      /* out (SDQLB200_F_KERNEL_TIMES): CUDA-event time of each launch   */
 } sdqlb200_args;
 
 int sdqlb200_num_queries(void);

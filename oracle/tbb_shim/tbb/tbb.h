@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstddef>
+#include <cstdlib>
 #include <deque>
 #include <functional>
 #include <mutex>
@@ -57,7 +58,13 @@ inline size_t run_chunks(size_t b, size_t e, size_t nchunks, F&& fn) {
 }  // namespace shim
 
 struct task_scheduler_init {
-    explicit task_scheduler_init(int n) { shim::nthreads() = n > 0 ? n : 1; }
+    // thread count: the generator bakes N in at compile time (sdql_compiler.py:485); SDQL_REF_THREADS overrides it
+    // at load time so one multi-threaded build can be timed on whatever core count the box has.
+    explicit task_scheduler_init(int n) {
+        const char* e = std::getenv("SDQL_REF_THREADS");
+        if (e && std::atoi(e) > 0) n = std::atoi(e);
+        shim::nthreads() = n > 0 ? n : 1;
+    }
 };
 
 template <class T>

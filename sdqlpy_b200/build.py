@@ -16,7 +16,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 INC = os.path.join(ROOT, "include")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--use_fast_math=false",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 
 
@@ -96,7 +96,10 @@ def compile_file(script_path, force=False, verbose=False):
     cu, so = out_paths(script_path)
     os.makedirs(os.path.dirname(cu), exist_ok=True)
     source = open(script_path).read()
-    text, _ = compile_source(source, os.path.relpath(script_path, ROOT) if script_path.startswith(ROOT) else script_path)
+    text, queries = compile_source(source, os.path.relpath(script_path, ROOT) if script_path.startswith(ROOT) else script_path)
+    import json
+    json.dump({"queries": [codegen.manifest_of(q) for q in queries]},
+              open(os.path.join(os.path.dirname(cu), "manifest.json"), "w"), indent=1)
     digest = hashlib.sha256(text.encode()).hexdigest()
     stamp = so + ".sha256"
     deps = [os.path.join(CSRC, f) for f in ("sdqlb200_rt.cuh", "sdqlb200_host.h")] + [os.path.join(INC, "sdqlb200.h")]

@@ -1484,7 +1484,8 @@ def render_query(q):
     L.append("    SDQL_CUDA(cudaMemsetAsync(a->workspace, 0, zero_end, st));")
     for ti in range(nt):
         L.append("    SDQL_CUDA(cudaMemsetAsync((char*)a->workspace + ff_off[%d], 0xFF, ff_len[%d], st));" % (ti, ti))
-    L.append("    int launches = 0;")
+    L.append("    int launches = 0; const bool kt = (a->flags & SDQLB200_F_KERNEL_TIMES) != 0;")
+    L.append("    if (kt) SDQL_CUDA(cudaEventRecord(sdqlhost_kev(0), st));")
     for K in q.kernels:
         if K.tiered:
             nf, tn = K.smem_nf, K.smem_tbl
@@ -1510,6 +1511,7 @@ def render_query(q):
         else:
             L.append("    SDQL_LAUNCH(%s, g_%s, sdqlrt::kBlock, 0, st, c);" % (K.name, K.name))
         L.append("    SDQL_CUDA(cudaGetLastError()); ++launches;")
+        L.append("    if (kt && launches < 24) SDQL_CUDA(cudaEventRecord(sdqlhost_kev(launches), st));")
     L.append("    SDQL_CUDA(cudaEventRecord(sdqlhost_ev(1), st));")
     L.append("    a->launches = launches;")
     L.append("    long long* rcols[%d] = {%s};" % (max(1, nres), ", ".join("c.res%d" % j for j in range(nres)) or "nullptr"))
@@ -1543,6 +1545,12 @@ static cudaEvent_t sdqlhost_ev(int i) {
     if (!g_ev_init) { cudaEventCreate(&g_ev[0]); cudaEventCreate(&g_ev[1]); g_ev_init = true; }
     return g_ev[i];
 }
+static cudaEvent_t g_kev[25];
+static bool g_kev_init = false;
+static cudaEvent_t sdqlhost_kev(int i) {
+    if (!g_kev_init) { for (int k = 0; k < 25; ++k) cudaEventCreate(&g_kev[k]); g_kev_init = true; }
+    return g_kev[i];
+}
 static int sdqlhost_sms() {
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms < 1) sms = 148; }
@@ -1559,6 +1567,8 @@ static int sdqlhost_fetch(sdqlb200_args* a, cudaStream_t st, unsigned long long*
     float ms = 0;
     cudaEventElapsedTime(&ms, sdqlhost_ev(0), sdqlhost_ev(1));
     a->device_ms = ms;
+    if (a->flags & SDQLB200_F_KERNEL_TIMES)
+        for (int k = 0; k < a->launches && k < 24; ++k) cudaEventElapsedTime(&a->kernel_ms[k], sdqlhost_kev(k), sdqlhost_kev(k + 1));
     if ((long long)cnt > cap) return sdqlhost::fail(SDQLB200_E_ARG, "result overflow: %%llu rows > capacity %%lld", cnt, cap);
     a->result.count = (long long)cnt;
     a->result.nfields = nf;

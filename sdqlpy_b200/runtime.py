@@ -21,6 +21,7 @@ from . import build
 KIND_ID = {"i32": 0, "f64": 1, "code": 2, "bytes": 3}
 E_WORKSPACE = -1
 F_NOFETCH = 1
+F_KERNEL_TIMES = 2
 
 
 class Col(ctypes.Structure):
@@ -39,7 +40,8 @@ class Args(ctypes.Structure):
                 ("nconsts", ctypes.c_int32), ("flags", ctypes.c_int32), ("workspace", ctypes.c_void_p),
                 ("workspace_bytes", ctypes.c_uint64), ("workspace_needed", ctypes.c_uint64),
                 ("stream", ctypes.c_void_p), ("device_ms", ctypes.c_float), ("launches", ctypes.c_int32),
-                ("tier", ctypes.c_int32), ("reserved", ctypes.c_int32), ("result", Result)]
+                ("tier", ctypes.c_int32), ("reserved", ctypes.c_int32), ("result", Result),
+                ("kernel_ms", ctypes.c_float * 24)]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -57,9 +59,21 @@ class CudaBackend:
         self.dev = torch.device("cuda", torch.cuda.current_device())
 
     def upload(self, arr):
-        t = self.torch.from_numpy(np.ascontiguousarray(arr))
-        d = t.to(self.dev, non_blocking=False)
+        """host -> device copy on the current stream (asynchronous when the host buffer is pinned)."""
+        arr = np.ascontiguousarray(arr)
+        if arr.nbytes == 0:
+            return self.alloc(256)
+        t = self.torch.from_numpy(arr)
+        d = self.torch.empty(t.shape, dtype=t.dtype, device=self.dev)
+        d.copy_(t, non_blocking=t.is_pinned())
         return d.data_ptr(), d
+
+    def pinned_like(self, arr):
+        """copy of a numpy array in page-locked host memory (numpy view, backing tensor)."""
+        t = self.torch.empty(arr.shape, dtype=self.torch.from_numpy(arr[:0]).dtype, pin_memory=True)
+        v = t.numpy()
+        v[...] = arr
+        return v, t
 
     def alloc(self, nbytes):
         d = self.torch.empty(max(int(nbytes), 256), dtype=self.torch.uint8, device=self.dev)
@@ -308,9 +322,9 @@ class CompiledModule:
         a.consts, a.nconsts = karr, len(consts)
         return a, (cols, carr, narr, karr)
 
-    def execute(self, name, a, fetch=True):
+    def execute(self, name, a, fetch=True, kernel_times=False):
         be = backend()
-        a.flags = 0 if fetch else F_NOFETCH
+        a.flags = (0 if fetch else F_NOFETCH) | (F_KERNEL_TIMES if kernel_times else 0)
         a.stream = be.stream()
         a.workspace, a.workspace_bytes = (self.ws[0] if self.ws else None), self.ws_bytes
         rc = self.lib.sdqlb200_run(name.encode(), ctypes.byref(a))

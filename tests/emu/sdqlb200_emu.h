@@ -53,6 +53,7 @@ static unsigned long long emu_dyn_smem[1 << 16];
 // host-driver stubs
 typedef int cudaEvent_t;
 static inline cudaEvent_t sdqlhost_ev(int) { return 0; }
+static inline cudaEvent_t sdqlhost_kev(int) { return 0; }
 static inline int cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 static inline int cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
 static inline int sdqlhost_sms() { return 1; }

@@ -1,0 +1,52 @@
+"""parity of the sm_100a build: every query through the C ABI on cuda:0 vs (a) the committed golden outputs of the
+real reference and (b) the real reference module itself (oracle/_ref, travels with the repo) on the same inputs."""
+import pytest
+
+from compare import compare
+from util import QUERIES, QUERY_SCRIPT, compact_db, golden, ref_db
+
+import ref_runner as rr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mod():
+    from sdqlpy_b200 import runtime
+    runtime.set_backend(None)
+    runtime.STORE.clear()
+    return runtime.load_compiled(QUERY_SCRIPT)
+
+
+@pytest.mark.parametrize("q", QUERIES)
+def test_golden_sf001(mod, q):
+    assert compare(mod.run(q, compact_db(0.01, rr.QUERY_ARGS[q])), golden(0.01)[q]) is None
+
+
+@pytest.mark.parametrize("q", QUERIES)
+def test_golden_sf005(mod, q):
+    assert compare(mod.run(q, compact_db(0.05, rr.QUERY_ARGS[q])), golden(0.05)[q]) is None
+
+
+@pytest.mark.parametrize("q", QUERIES)
+def test_reference_module_sf05(mod, q):
+    """same seeded inputs through the reference's generated C++ (1 thread) and through the CUDA path."""
+    if not rr.available("tpchref_sf1_t1"):
+        pytest.skip("oracle/_ref not built")
+    ref = rr.load("tpchref_sf1_t1")
+    want = rr.run(ref, q, ref_db(0.5, rr.QUERY_ARGS[q]))
+    got = mod.run(q, compact_db(0.5, rr.QUERY_ARGS[q]))
+    assert compare(got, want) is None
+
+
+@pytest.mark.parametrize("q", ["q1", "q6", "q3", "q12", "q19"])
+def test_reference_layout_inputs(mod, q):
+    """the reference's own input layout (int64 / float64 / <U n numpy arrays) through the boundary."""
+    assert compare(mod.run(q, ref_db(0.05, rr.QUERY_ARGS[q])), golden(0.05)[q]) is None
+
+
+def test_run_to_run_determinism_of_reductions(mod):
+    db = compact_db(0.05, ["lineitem"])
+    a = mod.run("q6", db)
+    for _ in range(3):
+        assert mod.run("q6", db) == a
