@@ -340,37 +340,62 @@ class Kernel:
                  (tmpl, self.name, q.name))
         L += ["    " + s for s in self.pre]
         if self.src[0] == "rel":
+            # software-pipelined streaming loop: the next group's column loads are issued before the current
+            # group is processed, so every thread keeps two groups (2 x 4 rows x all columns) in flight
+            ety = {"i32": "int", "f64": "double", "code": "int"}
+
+            def loads(prefix, gvar, ind):
+                o = []
+                o.append(ind + "{")
+                o.append(ind + "    const long long j0 = %s << 2;" % gvar)
+                o.append(ind + "    if (j0 + 4 <= n) {")
+                for (col, rep), (arr, idx) in self.scan_cols.items():
+                    dst = prefix + arr[2:]
+                    if rep == "code":
+                        o.append(ind + "        sdqlrt::ld4_code(c.in%d, j0, c.in%d_w, %s);" % (idx, idx, dst))
+                    else:
+                        o.append(ind + "        sdqlrt::ld4(c.in%d + j0, %s);" % (idx, dst))
+                o.append(ind + "    } else {")
+                o.append(ind + "        for (int u = 0; u < 4; ++u) {")
+                o.append(ind + "            const long long ii = (j0 + u < n) ? j0 + u : n - 1;")
+                for (col, rep), (arr, idx) in self.scan_cols.items():
+                    dst = prefix + arr[2:]
+                    if rep == "code":
+                        o.append(ind + "            %s[u] = sdqlrt::ld1_code(c.in%d, ii, c.in%d_w);" % (dst, idx, idx))
+                    else:
+                        o.append(ind + "            %s[u] = sdqlrt::ld1(c.in%d + ii);" % (dst, idx))
+                o.append(ind + "        }")
+                o.append(ind + "    }")
+                o.append(ind + "}")
+                return o
+
             L.append("    const long long n = c.n_%s;" % self.src[1])
             L.append("    const long long ngrp = (n + 3) >> 2;")
-            L.append("    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ngrp; "
-                     "g += (long long)gridDim.x * blockDim.x) {")
+            L.append("    const long long gstride = (long long)gridDim.x * blockDim.x;")
+            L.append("    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
+            for (col, rep), (arr, idx) in self.scan_cols.items():
+                L.append("    %s %s[4], %s[4];" % (ety[rep], arr, "q_" + arr[2:]))
+            L.append("    if (g < ngrp)")
+            L += loads("r_", "g", "    ")
+            L.append("    while (g < ngrp) {")
+            L.append("        const long long gn = g + gstride;")
+            L.append("        if (gn < ngrp)")
+            L += loads("q_", "gn", "        ")
             L.append("        const long long i0 = g << 2;")
-            for (col, rep), (arr, idx) in self.scan_cols.items():
-                ety = {"i32": "int", "f64": "double", "code": "int"}[rep]
-                L.append("        %s %s[4];" % (ety, arr))
-            L.append("        if (i0 + 4 <= n) {")
-            for (col, rep), (arr, idx) in self.scan_cols.items():
-                if rep == "code":
-                    L.append("            sdqlrt::ld4_code(c.in%d, i0, c.in%d_w, %s);" % (idx, idx, arr))
-                else:
-                    L.append("            sdqlrt::ld4(c.in%d + i0, %s);" % (idx, arr))
-            L.append("        } else {")
-            L.append("            for (int u = 0; u < 4; ++u) {")
-            L.append("                const long long ii = (i0 + u < n) ? i0 + u : n - 1;")
-            for (col, rep), (arr, idx) in self.scan_cols.items():
-                if rep == "code":
-                    L.append("                %s[u] = sdqlrt::ld1_code(c.in%d, ii, c.in%d_w);" % (arr, idx, idx))
-                else:
-                    L.append("                %s[u] = sdqlrt::ld1(c.in%d + ii);" % (arr, idx))
-            L.append("            }")
-            L.append("        }")
             L.append("#pragma unroll")
             L.append("        for (int u = 0; u < 4; ++u) {")
             L.append("            const long long i = i0 + u;")
             L.append("            if (i < n) {")
-            L += ["                " + s for s in self.body]
+            L += ["                " + x for x in self.body]
             L.append("            }")
             L.append("        }")
+            L.append("        g = gn;")
+            if self.scan_cols:
+                L.append("#pragma unroll")
+                L.append("        for (int u = 0; u < 4; ++u) {")
+                for (col, rep), (arr, idx) in self.scan_cols.items():
+                    L.append("            %s[u] = %s[u];" % (arr, "q_" + arr[2:]))
+                L.append("        }")
             L.append("    }")
         elif self.src[0] == "tbl":
             t = self.src[1]
@@ -1495,12 +1520,12 @@ def render_query(q):
             L.append("        else if (c.%s.direct && cap * (%d * 8 + 4) <= 65536) { tier = 1; smem = (size_t)cap * (%d * 8 + 4); }" % (tn, nf, nf))
             L.append("        if (tier == 0) {")
             L.append("            SDQL_CUDA(cudaFuncSetAttribute(%s<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));" % K.name)
-            L.append("            int cps = (int)(200000 / (smem + 1024)); if (cps < 1) cps = 1; if (cps > 8) cps = 8;")
+            L.append("            int cps = (int)(232448 / (smem + 1024)); if (cps < 1) cps = 1; if (cps > 8) cps = 8;")
             L.append("            g_%s = sdqlhost::grid_for(w_%s, cps, sms);" % (K.name, K.name))
             L.append("            SDQL_LAUNCH(%s<0>, g_%s, sdqlrt::kBlock, smem, st, c);" % (K.name, K.name))
             L.append("        } else if (tier == 1) {")
             L.append("            SDQL_CUDA(cudaFuncSetAttribute(%s<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));" % K.name)
-            L.append("            int cps = (int)(200000 / (smem + 1024)); if (cps < 1) cps = 1; if (cps > 8) cps = 8;")
+            L.append("            int cps = (int)(232448 / (smem + 1024)); if (cps < 1) cps = 1; if (cps > 8) cps = 8;")
             L.append("            g_%s = sdqlhost::grid_for(w_%s, cps, sms);" % (K.name, K.name))
             L.append("            SDQL_LAUNCH(%s<1>, g_%s, sdqlrt::kBlock, smem, st, c);" % (K.name, K.name))
             L.append("        } else {")

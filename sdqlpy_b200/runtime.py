@@ -304,7 +304,11 @@ class CompiledModule:
             cols.append(STORE.get(db[argpos[arg]][names.index(col)], rep, width))
         nrows = []
         for a in q["args"]:
-            first = db[argpos[a]][0]
+            # row count: first available column (the reference reads it from column 0, sdql_compiler.py:644)
+            present = [c for c in db[argpos[a]] if c is not None]
+            if not present:
+                raise ValueError("%s: relation '%s' has no columns" % (name, a))
+            first = present[0]
             nrows.append(first.rows if isinstance(first, DeviceColumn) else
                          (first.data.shape[0] if hasattr(first, "kind") else len(first)))
         consts = []
