@@ -21,6 +21,11 @@ extern "C" {
 enum { SDQLB200_I32 = 0, SDQLB200_F64 = 1, SDQLB200_CODE = 2, SDQLB200_BYTES = 3 };
 enum { SDQLB200_OK = 0, SDQLB200_E_WORKSPACE = -1, SDQLB200_E_CUDA = -2, SDQLB200_E_ARG = -3, SDQLB200_E_NOQUERY = -4 };
 enum { SDQLB200_F_NOFETCH = 1, SDQLB200_F_KERNEL_TIMES = 2 };
+enum { SDQLB200_COL_PARTKEY = 1 };                       /* sdqlb200_col.flags: the relation is range partitioned on this column */
+enum { SDQLB200_SUM_F64 = 0, SDQLB200_SUM_I64 = 1, SDQLB200_MIN_I32 = 2 }; /* merge ops */
+/* multi-GPU: called (stream ordered) after a kernel over a partitioned relation for every partial buffer that has to
+ * be combined across ranks; the callee all-reduces `count` elements at workspace + offset in place (NCCL).  */
+typedef int (*sdqlb200_merge_fn)(void* ctx, uint64_t workspace_offset, uint64_t count, int32_t op);
 
 /* one device-resident column (replaces the borrowed numpy buffer of sdql_compiler.py:653-668) */
 typedef struct {
@@ -29,6 +34,8 @@ typedef struct {
     int64_t min, max; /* value range of int/date columns; [0, dictionary size - 1] for codes    */
     int32_t width;    /* element bytes: I32 4, F64 8, CODE 1 or 4, BYTES = fixed string width   */
     int32_t kind;     /* SDQLB200_I32 | F64 | CODE | BYTES                                       */
+    int32_t flags;    /* SDQLB200_COL_*                                                          */
+    int32_t reserved;
 } sdqlb200_col;
 
 /* result rows in SoA form; every field is one 8-byte slot per row (int64 / fp64 bits / string reference) */
@@ -57,6 +64,12 @@ typedef struct {
     int32_t reserved;
     sdqlb200_result result;   /* out                                                            */
     float kernel_ms[24];      /* out (SDQLB200_F_KERNEL_TIMES): CUDA-event time of each launch   */
+    sdqlb200_merge_fn merge;  /* NULL on a single GPU                                           */
+    void* merge_ctx;
+    uint32_t part_mask;       /* bit i set: relation argument i holds only this rank's partition */
+    int32_t result_partial;   /* out: 1 = result rows are this rank's share (concatenate ranks) */
+    int32_t rank;             /* this process' rank among the GPUs (0 on a single GPU)          */
+    int32_t reserved2;
 } sdqlb200_args;
 
 int sdqlb200_num_queries(void);

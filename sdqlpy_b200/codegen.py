@@ -24,6 +24,7 @@ provenance, which is what allows group keys to be minimised by functional depend
 on the host until the result is boxed (late materialisation by row id).
 """
 import json
+import os
 from collections import OrderedDict
 
 from . import ir
@@ -33,6 +34,12 @@ from .ir import ExtFuncSymbol as XF
 
 class CodegenError(Exception):
     pass
+
+
+# scan-loop latency hiding: "reg" = double-buffer the next row group in registers; "l2" = single register buffer
+# plus prefetch.global.L2 of the group PF_DIST iterations ahead (fewer registers -> more resident warps)
+PIPELINE = os.environ.get("SDQLB200_PIPELINE", "reg")
+PF_DIST = int(os.environ.get("SDQLB200_PF_DIST", "2"))
 
 
 # =============================================================================================
@@ -373,14 +380,28 @@ class Kernel:
             L.append("    const long long ngrp = (n + 3) >> 2;")
             L.append("    const long long gstride = (long long)gridDim.x * blockDim.x;")
             L.append("    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
-            for (col, rep), (arr, idx) in self.scan_cols.items():
-                L.append("    %s %s[4], %s[4];" % (ety[rep], arr, "q_" + arr[2:]))
-            L.append("    if (g < ngrp)")
-            L += loads("r_", "g", "    ")
-            L.append("    while (g < ngrp) {")
-            L.append("        const long long gn = g + gstride;")
-            L.append("        if (gn < ngrp)")
-            L += loads("q_", "gn", "        ")
+            if PIPELINE == "reg":
+                for (col, rep), (arr, idx) in self.scan_cols.items():
+                    L.append("    %s %s[4], %s[4];" % (ety[rep], arr, "q_" + arr[2:]))
+                L.append("    if (g < ngrp)")
+                L += loads("r_", "g", "    ")
+                L.append("    while (g < ngrp) {")
+                L.append("        const long long gn = g + gstride;")
+                L.append("        if (gn < ngrp)")
+                L += loads("q_", "gn", "        ")
+            else:  # "l2": single register buffer, the group PF_DIST iterations ahead is prefetched into L2
+                for (col, rep), (arr, idx) in self.scan_cols.items():
+                    L.append("    %s %s[4];" % (ety[rep], arr))
+                L.append("    while (g < ngrp) {")
+                L.append("        const long long gn = g + gstride;")
+                L.append("        { const long long gp = g + %d * gstride; if (gp < ngrp) {" % PF_DIST)
+                for (col, rep), (arr, idx) in self.scan_cols.items():
+                    if rep == "code":
+                        L.append("            sdqlrt::prefetch_l2((const char*)c.in%d + (gp << 2) * c.in%d_w);" % (idx, idx))
+                    else:
+                        L.append("            sdqlrt::prefetch_l2(c.in%d + (gp << 2));" % idx)
+                L.append("        } }")
+                L += loads("r_", "g", "        ")
             L.append("        const long long i0 = g << 2;")
             L.append("#pragma unroll")
             L.append("        for (int u = 0; u < 4; ++u) {")
@@ -390,7 +411,7 @@ class Kernel:
             L.append("            }")
             L.append("        }")
             L.append("        g = gn;")
-            if self.scan_cols:
+            if self.scan_cols and PIPELINE == "reg":
                 L.append("#pragma unroll")
                 L.append("        for (int u = 0; u < 4; ++u) {")
                 for (col, rep), (arr, idx) in self.scan_cols.items():
@@ -603,21 +624,23 @@ class GroupSink(KeyedSink):
         vals = [cast_to(x, ct) for (n, x), (_, ct) in zip(items, t.fields)]
         if self.tiered:
             K.emit("if (TIER == 0) {")
+            K.emit("    const int sb = (int)%s * %d * (int)blockDim.x + (int)threadIdx.x;" % (kk, nf))
             for j, (_, ct) in enumerate(t.fields):
-                idx = "((%s * %d + %d) * blockDim.x + threadIdx.x)" % (kk, nf, j)
+                idx = "sb + %d * (int)blockDim.x" % j
                 if ct == "f64":
                     K.emit("    sm[%s] = __double_as_longlong(__longlong_as_double(sm[%s]) + %s);" % (idx, idx, vals[j]))
                 else:
                     K.emit("    sm[%s] += (unsigned long long)(%s);" % (idx, vals[j]))
-            K.emit("    smrep[%s * blockDim.x + threadIdx.x] = (int)%s;" % (kk, K.scan_var))
+            K.emit("    smrep[(int)%s * (int)blockDim.x + (int)threadIdx.x] = (int)%s;" % (kk, K.scan_var))
             K.emit("} else if (TIER == 1) {")
+            K.emit("    const int sb = (int)%s * %d;" % (kk, nf))
             for j, (_, ct) in enumerate(t.fields):
-                idx = "(%s * %d + %d)" % (kk, nf, j)
+                idx = "sb + %d" % j
                 if ct == "f64":
                     K.emit("    atomicAdd((double*)&sm[%s], %s);" % (idx, vals[j]))
                 else:
                     K.emit("    atomicAdd(&sm[%s], (unsigned long long)(%s));" % (idx, vals[j]))
-            K.emit("    smrep[%s] = (int)%s;" % (kk, K.scan_var))
+            K.emit("    smrep[(int)%s] = (int)%s;" % (kk, K.scan_var))
             K.emit("} else {")
             K.depth += 1
         K.emit("bool nw; const int sl = sdqlrt::tbl_upsert(c.%s, %s, (int)%s, nw);" % (t.name, kk, K.scan_var))
@@ -821,6 +844,7 @@ class Query:
 
     def new_table(self, kind):
         t = TableDesc(self, "t%d" % len(self.tables), kind)
+        t.builder = None
         self.tables.append(t)
         return t
 
@@ -979,6 +1003,9 @@ class Query:
         self.add_kernel(K)
 
     def add_kernel(self, K):
+        for t in self.tables:
+            if t.builder is None and t.src is not None:
+                t.builder = K  # tables are sized/created in order, a kernel owns the tables made since the last one
         self.kernels.append(K)
         self.steps.append(("launch", K))
 
@@ -1408,6 +1435,49 @@ def _stats_exprs(st):
     return "0ll", "-1ll"
 
 
+def part_expr(K):
+    if K.src[0] == "rel":
+        return "part_%s" % K.name
+    if K.src[0] == "tbl":
+        return "part_%s" % K.src[1].name
+    return "false"
+
+
+def merge_code(q, K):
+    """host code after the launch of K: combine this rank's partial outputs with the other ranks' (SURVEY.md 8e).
+    Scalars and direct-indexed tables are all-reduced in place through the caller's merge callback; a table keyed by
+    the partitioning column stays rank-local (co-partitioned) and marks its consumers as partial instead."""
+    L = []
+    pe = part_expr(K)
+    if pe == "false":
+        return L
+    L.append("    if (%s) {" % pe)
+    off = "(unsigned long long)((char*)(%s) - (char*)a->workspace)"
+    sinks = [K.sink] if K.sink is not None else []
+    for sk in sinks:
+        if isinstance(sk, ReduceSink):
+            for f in sk.fields:
+                L.append("        if (a->merge(a->merge_ctx, %s, 1, %s)) return sdqlhost::fail(SDQLB200_E_ARG, \"merge callback failed\");" %
+                         (off % ("c.sc + %d" % f[2]), "SDQLB200_SUM_F64" if f[1] == "f64" else "SDQLB200_SUM_I64"))
+    for t in q.tables:
+        if t.builder is not K:
+            continue
+        cop = " || ".join("((a->cols[%d].flags & SDQLB200_COL_PARTKEY) != 0)" % p[1] for p in t.parts if p[0] == "col") or "false"
+        L.append("        part_%s = true;  // iteration over this table is partitioned (by key range or by owner rank)" % t.name)
+        L.append("        if (!(%s)) {" % cop)
+        L.append("            if (!c.%s.direct) return sdqlhost::fail(SDQLB200_E_ARG, \"%s: table %s is hashed; cross-GPU shuffle of hashed partial tables is not implemented\");" % (t.name, q.name, t.name))
+        L.append("            const int og = sdqlhost::grid_for(c.%s.cap, 8, sms);" % t.name)
+        L.append("            SDQL_LAUNCH(sdqlrt::k_owner_encode, og, sdqlrt::kBlock, 0, st, c.%s.rep, own_%s, c.%s.cap, a->rank);" % (t.name, t.name, t.name))
+        L.append("            if (a->merge(a->merge_ctx, %s, (unsigned long long)c.%s.cap, SDQLB200_MIN_I32)) return sdqlhost::fail(SDQLB200_E_ARG, \"merge callback failed\");" % (off % ("own_%s" % t.name), t.name))
+        L.append("            SDQL_LAUNCH(sdqlrt::k_owner_decode, og, sdqlrt::kBlock, 0, st, c.%s.rep, own_%s, c.%s.cap, a->rank);" % (t.name, t.name, t.name))
+        for j, (_, ct) in enumerate(t.fields):
+            L.append("            if (a->merge(a->merge_ctx, %s, (unsigned long long)c.%s.cap, %s)) return sdqlhost::fail(SDQLB200_E_ARG, \"merge callback failed\");" %
+                     (off % ("c.%s_a%d" % (t.name, j)), t.name, "SDQLB200_SUM_F64" if ct == "f64" else "SDQLB200_SUM_I64"))
+        L.append("        }")
+    L.append("    }")
+    return L
+
+
 def render_query(q):
     """-> CUDA text of one query: context struct, kernels, host driver."""
     n = q.name
@@ -1480,6 +1550,8 @@ def render_query(q):
         for j, (_, ct) in enumerate(t.fields):
             L.append("        c.%s_a%d = ar.alloc<%s>(c.%s.cap);" % (t.name, j, CT[ct], t.name))
         L.append("    }")
+    for t in q.tables:
+        L.append("    int* own_%s = a->merge ? ar.alloc<int>(c.%s.cap) : nullptr;" % (t.name, t.name))
     L.append("    c.sc = ar.alloc<double>(%d); c.cnt = ar.alloc<unsigned>(%d);" % (max(1, q.nsc), max(1, q.ncnt)))
     # grids
     for K in q.kernels:
@@ -1510,6 +1582,12 @@ def render_query(q):
     for ti in range(nt):
         L.append("    SDQL_CUDA(cudaMemsetAsync((char*)a->workspace + ff_off[%d], 0xFF, ff_len[%d], st));" % (ti, ti))
     L.append("    int launches = 0; const bool kt = (a->flags & SDQLB200_F_KERNEL_TIMES) != 0;")
+    L.append("    const unsigned pm = a->merge ? a->part_mask : 0u;  // multi-GPU: which relation arguments are partitioned")
+    for t in q.tables:
+        L.append("    bool part_%s = false;" % t.name)
+    for K in q.kernels:
+        if K.src[0] == "rel":
+            L.append("    const bool part_%s = (pm >> %d) & 1u;" % (K.name, q.args.index(K.src[1])))
     L.append("    if (kt) SDQL_CUDA(cudaEventRecord(sdqlhost_kev(0), st));")
     for K in q.kernels:
         if K.tiered:
@@ -1536,9 +1614,11 @@ def render_query(q):
         else:
             L.append("    SDQL_LAUNCH(%s, g_%s, sdqlrt::kBlock, 0, st, c);" % (K.name, K.name))
         L.append("    SDQL_CUDA(cudaGetLastError()); ++launches;")
+        L += merge_code(q, K)
         L.append("    if (kt && launches < 24) SDQL_CUDA(cudaEventRecord(sdqlhost_kev(launches), st));")
     L.append("    SDQL_CUDA(cudaEventRecord(sdqlhost_ev(1), st));")
     L.append("    a->launches = launches;")
+    L.append("    a->result_partial = %s ? 1 : 0;" % part_expr(q.kernels[-1]))
     L.append("    long long* rcols[%d] = {%s};" % (max(1, nres), ", ".join("c.res%d" % j for j in range(nres)) or "nullptr"))
     L.append("    return sdqlhost_fetch(a, st, c.res_count, c.res_cap, %d, rcols);" % nres)
     L.append("}")

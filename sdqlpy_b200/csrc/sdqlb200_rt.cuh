@@ -54,7 +54,9 @@ SDQL_DEV void ld4(const unsigned char* p, int (&v)[4]) {
     v[0] = w & 0xff; v[1] = (w >> 8) & 0xff; v[2] = (w >> 16) & 0xff; v[3] = w >> 24;
 }
 template <class T> SDQL_DEV T ld1(const T* p) { return __ldg(p); }
+SDQL_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p)); }
 #else
+SDQL_DEV void prefetch_l2(const void*) {}
 template <class T, class V> SDQL_DEV void ld4(const T* p, V (&v)[4]) { for (int k = 0; k < 4; ++k) v[k] = (V)p[k]; }
 template <class T> SDQL_DEV T ld1(const T* p) { return *p; }
 #endif
@@ -73,7 +75,8 @@ SDQL_DEV int ld1_code(const void* p, i64 i, int width) {
 // ---------------------------------------------------------------------------------------------
 struct Tbl {
     u64* keys;   // hash mode: packed key per slot (kEmpty = free); unused in direct mode
-    int* rep;    // representative source index (row of the scanned relation / slot of the scanned table); -1 = free
+    int* rep;    // representative source index (row of the scanned relation / slot of the scanned table); -1 = free;
+                 // after a cross-GPU merge: -2 = present but owned (iterated, late-materialised) by another rank
     i64 cap;     // slots (direct: key domain size; hash: power of two)
     int direct;  // 1: slot == packed key
 };
@@ -86,7 +89,7 @@ SDQL_DEV u64 hash64(u64 x) {  // splitmix64 finaliser
 // -> slot or -1.  `ok` = every key part was inside the table's packing range.
 SDQL_DEV int tbl_find(const Tbl& t, u64 key, bool ok) {
     if (!ok) return -1;
-    if (t.direct) return ld1(t.rep + key) >= 0 ? (int)key : -1;
+    if (t.direct) return ld1(t.rep + key) != -1 ? (int)key : -1;  // -2 = present, owned by another rank
     u64 m = (u64)t.cap - 1, h = hash64(key) & m;
     for (;;) {
         u64 k = ld1(t.keys + h);
@@ -210,6 +213,21 @@ SDQL_DEV bool last_block(unsigned* counter) {
 #else
     return true;
 #endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross-GPU merge of a direct-indexed table: every occupied slot gets exactly one owner rank (the lowest rank that
+// saw the key); aggregate arrays are all-reduced separately.  encode -> all-reduce(min) -> decode.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_owner_encode(const int* rep, int* own, long long cap, int rank) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (long long)gridDim.x * blockDim.x)
+        own[i] = rep[i] >= 0 ? rank : 0x7fffffff;
+}
+__global__ void k_owner_decode(int* rep, const int* own, long long cap, int rank) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (long long)gridDim.x * blockDim.x) {
+        const int o = own[i];
+        if (o != rank) rep[i] = (o == 0x7fffffff) ? -1 : -2;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -26,7 +26,7 @@ F_KERNEL_TIMES = 2
 
 class Col(ctypes.Structure):
     _fields_ = [("data", ctypes.c_void_p), ("rows", ctypes.c_int64), ("min", ctypes.c_int64), ("max", ctypes.c_int64),
-                ("width", ctypes.c_int32), ("kind", ctypes.c_int32)]
+                ("width", ctypes.c_int32), ("kind", ctypes.c_int32), ("flags", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class Result(ctypes.Structure):
@@ -41,7 +41,12 @@ class Args(ctypes.Structure):
                 ("workspace_bytes", ctypes.c_uint64), ("workspace_needed", ctypes.c_uint64),
                 ("stream", ctypes.c_void_p), ("device_ms", ctypes.c_float), ("launches", ctypes.c_int32),
                 ("tier", ctypes.c_int32), ("reserved", ctypes.c_int32), ("result", Result),
-                ("kernel_ms", ctypes.c_float * 24)]
+                ("kernel_ms", ctypes.c_float * 24), ("merge", ctypes.c_void_p), ("merge_ctx", ctypes.c_void_p),
+                ("part_mask", ctypes.c_uint32), ("result_partial", ctypes.c_int32), ("rank", ctypes.c_int32),
+                ("reserved2", ctypes.c_int32)]
+
+
+MERGE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int32)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -122,13 +127,20 @@ def _ustr_to_bytes(a, width):
     return out
 
 
+_STATS = {}  # id(Column) -> (Column, min, max): value ranges are properties of the data, computed once
+
+
 def _encode(src, rep, width):
     """host column (numpy array or tpch.gen.Column) -> (numpy device image, min, max, elem width, dictionary)."""
     from .tpch.gen import Column
     if isinstance(src, Column):
         if rep == "i32":
             a = src.data.astype(np.int32, copy=False)
-            return a, int(a.min()) if len(a) else 0, int(a.max()) if len(a) else 0, 4, None
+            st = _STATS.get(id(src))
+            if st is None or st[0] is not src:
+                st = (src, int(a.min()) if len(a) else 0, int(a.max()) if len(a) else 0)
+                _STATS[id(src)] = st
+            return a, st[1], st[2], 4, None
         if rep == "f64":
             return src.data.astype(np.float64, copy=False), 0, 0, 8, None
         if rep == "code":
@@ -215,6 +227,36 @@ class ColumnStore:
 STORE = ColumnStore()
 
 
+class DistConfig:
+    """multi-GPU execution (one process per GPU, torch.distributed): which relation arguments are range
+    partitioned across ranks and which columns they are partitioned on."""
+
+    def __init__(self, partitioned=("li", "ord"), partkeys=("l_orderkey", "o_orderkey"), group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.partitioned, self.partkeys = set(partitioned), set(partkeys)
+        self.stats = {}
+
+    def global_range(self, key, mn, mx):
+        """column statistics must agree on all ranks: merged tables use them as packing radices."""
+        import torch
+        if key not in self.stats:
+            dev = "cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu"
+            t = torch.tensor([-mn, mx], dtype=torch.int64, device=dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+            self.stats[key] = (-int(t[0]), int(t[1]))
+        return self.stats[key]
+
+
+DIST = None
+
+
+def set_distributed(cfg):
+    global DIST
+    DIST = cfg
+
+
 def host_strings(src, rows):
     """values of a host string column at the given row ids (late materialisation of string result fields)."""
     from .tpch.gen import Column
@@ -281,6 +323,7 @@ class CompiledModule:
         self.ws = None
         self.ws_bytes = 0
         self.last = None
+        self._merge_cb, self.merges, self.merge_error = None, 0, None
         for name in self.queries:
             setattr(self, name + "_compiled", self._make(name))
 
@@ -319,7 +362,16 @@ class CompiledModule:
         a = Args()
         carr = (Col * max(1, len(cols)))()
         for i, c in enumerate(cols):
-            carr[i] = Col(c.ptr, c.rows, c.min, c.max, c.width, KIND_ID[c.kind])
+            mn, mx, flags = c.min, c.max, 0
+            arg, cname, rep = q["inputs"][i]
+            if DIST is not None and DIST.world > 1 and arg in DIST.partitioned:
+                if rep == "i32":
+                    mn, mx = DIST.global_range((name, i), mn, mx)
+                if cname in DIST.partkeys:
+                    flags = 1
+            carr[i] = Col(c.ptr, c.rows, mn, mx, c.width, KIND_ID[c.kind], flags, 0)
+        if DIST is not None and DIST.world > 1:
+            a.part_mask = sum(1 << i for i, g in enumerate(q["args"]) if g in DIST.partitioned)
         narr = (ctypes.c_int64 * max(1, len(nrows)))(*nrows)
         karr = (ctypes.c_int64 * max(1, len(consts)))(*consts)
         a.cols, a.ncols, a.nargs, a.nrows = carr, len(cols), len(nrows), narr
@@ -331,6 +383,11 @@ class CompiledModule:
         a.flags = (0 if fetch else F_NOFETCH) | (F_KERNEL_TIMES if kernel_times else 0)
         a.stream = be.stream()
         a.workspace, a.workspace_bytes = (self.ws[0] if self.ws else None), self.ws_bytes
+        if DIST is not None and DIST.world > 1:
+            if self._merge_cb is None:
+                self._merge_cb = MERGE_FN(self._merge)
+            a.merge = ctypes.cast(self._merge_cb, ctypes.c_void_p)
+            a.rank = DIST.rank
         rc = self.lib.sdqlb200_run(name.encode(), ctypes.byref(a))
         if rc == E_WORKSPACE:
             need = int(a.workspace_needed)
@@ -340,8 +397,28 @@ class CompiledModule:
             a.workspace, a.workspace_bytes = self.ws[0], self.ws_bytes
             rc = self.lib.sdqlb200_run(name.encode(), ctypes.byref(a))
         if rc != 0:
-            raise RuntimeError("sdqlb200_run(%s) failed (%d): %s" % (name, rc, self.lib.sdqlb200_last_error().decode()))
+            extra = " [%r]" % (self.merge_error,) if self.merge_error is not None else ""
+            raise RuntimeError("sdqlb200_run(%s) failed (%d): %s%s" % (name, rc, self.lib.sdqlb200_last_error().decode(), extra))
         return a
+
+    def _merge(self, ctx, off, count, op):
+        """sdqlb200_merge_fn: all-reduce `count` elements at workspace + off in place (NCCL on GPUs, gloo in tests)."""
+        try:
+            import torch
+            d = DIST.dist
+            ws = self.ws[1]
+            t = ws if isinstance(ws, torch.Tensor) else torch.from_numpy(ws)
+            if op == 0:
+                d.all_reduce(t[off:off + 8 * count].view(torch.float64), op=d.ReduceOp.SUM, group=DIST.group)
+            elif op == 1:
+                d.all_reduce(t[off:off + 8 * count].view(torch.int64), op=d.ReduceOp.SUM, group=DIST.group)
+            else:
+                d.all_reduce(t[off:off + 4 * count].view(torch.int32), op=d.ReduceOp.MIN, group=DIST.group)
+            self.merges += 1
+            return 0
+        except Exception as e:  # never let an exception cross the C boundary
+            self.merge_error = e
+            return 1
 
     def run(self, name, db):
         h2d0 = STORE.h2d_bytes
@@ -356,7 +433,12 @@ class CompiledModule:
         info.device_ms, info.launches, info.tier = float(a.device_ms), int(a.launches), int(a.tier)
         info.workspace_bytes, info.h2d_bytes, info.d2h_bytes, info.rows = int(a.workspace_needed), STORE.h2d_bytes - h2d0, 8 + n * nf * 8, n
         self.last = info
-        return self.box(q, db, cols, n)
+        res = self.box(q, db, cols, n)
+        if int(a.result_partial) and DIST is not None and DIST.world > 1 and isinstance(res, ResultSet):
+            parts = [None] * DIST.world  # result rows are this rank's share: concatenate the ranks
+            DIST.dist.all_gather_object(parts, res.rows, group=DIST.group)
+            res = ResultSet(res.names, list(dict.fromkeys(r for p in parts for r in p)))
+        return res
 
     def box(self, q, db, cols, n):
         kind = q["result_kind"]
@@ -401,6 +483,7 @@ _modules = {}
 def load_compiled(script_path):
     """the module object the dispatcher imports as <script>_compiled (sdql_lib.py:401-402)."""
     _, so = build.out_paths(script_path)
+    so = os.environ.get("SDQLB200_SO", so)  # experiments: alternative build of the same module
     if so not in _modules:
         _modules[so] = CompiledModule(so)
     return _modules[so]

@@ -49,6 +49,7 @@ using std::min;
 static unsigned long long emu_dyn_smem[1 << 16];
 #define SDQL_EXTERN_SMEM(name) unsigned long long* name = emu_dyn_smem
 #define SDQL_LAUNCH(kernel, grid, block, smem, stream, ...) kernel(__VA_ARGS__)
+#define SDQL_UNUSED(x) (void)(x)
 
 // host-driver stubs
 typedef int cudaEvent_t;
