@@ -41,45 +41,42 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled through NVML in a background thread DURING the timed region."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu=0):
-        self.lines, self.proc, self.gpu = [], None, gpu
+        self.gpu, self.sm, self.mask, self.stop_flag, self.th, self.h = gpu, [], 0, False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.001)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+        if self.h is not None:
+            self.th = threading.Thread(target=self._loop, daemon=True)
+            self.th.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self.stop_flag = True
+        self.th.join()
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": float(self.max),
+                "samples": len(self.sm), "reasons": sorted(v for k, v in self.REASONS.items() if self.mask & k)}
 
 
 def scan_bytes_per_row(man, relation_arg):
@@ -168,6 +165,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from sdqlpy_b200 import runtime
+    if world > 1:  # lineitem is range partitioned on order boundaries across the ranks
+        runtime.set_distributed(runtime.DistConfig(partitioned=("li",), partkeys=("l_orderkey",)))
     mod = runtime.load_compiled(QUERY_SCRIPT)
     man = mod.queries[q]
     if man["args"] != ["li"]:
@@ -193,7 +192,8 @@ def main():
     torch.cuda.synchronize()
 
     def merge(res_rows):
-        """N > 1: exchange partial result rows (one NCCL all-gather), merge by key on every rank."""
+        """N > 1: partial tables were merged inside the query (all-reduce through the merge callback); every group is
+        emitted by its owner rank, so the result rows of the ranks are concatenated with one NCCL all-gather."""
         if world == 1:
             return res_rows
         buf = torch.zeros(64, 8, dtype=torch.int64, device="cuda")

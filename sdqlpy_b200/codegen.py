@@ -38,7 +38,7 @@ class CodegenError(Exception):
 
 # scan-loop latency hiding: "reg" = double-buffer the next row group in registers; "l2" = single register buffer
 # plus prefetch.global.L2 of the group PF_DIST iterations ahead (fewer registers -> more resident warps)
-PIPELINE = os.environ.get("SDQLB200_PIPELINE", "reg")
+PIPELINE = os.environ.get("SDQLB200_PIPELINE", "auto")  # auto: l2 for shared-memory-tiered or wide (>= 6 column) scans
 PF_DIST = int(os.environ.get("SDQLB200_PF_DIST", "2"))
 
 
@@ -380,7 +380,10 @@ class Kernel:
             L.append("    const long long ngrp = (n + 3) >> 2;")
             L.append("    const long long gstride = (long long)gridDim.x * blockDim.x;")
             L.append("    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
-            if PIPELINE == "reg":
+            pipe = PIPELINE
+            if pipe == "auto":
+                pipe = "l2" if (self.tiered or len(self.scan_cols) >= 6) else "reg"
+            if pipe == "reg":
                 for (col, rep), (arr, idx) in self.scan_cols.items():
                     L.append("    %s %s[4], %s[4];" % (ety[rep], arr, "q_" + arr[2:]))
                 L.append("    if (g < ngrp)")
@@ -411,7 +414,7 @@ class Kernel:
             L.append("            }")
             L.append("        }")
             L.append("        g = gn;")
-            if self.scan_cols and PIPELINE == "reg":
+            if self.scan_cols and pipe == "reg":
                 L.append("#pragma unroll")
                 L.append("        for (int u = 0; u < 4; ++u) {")
                 for (col, rep), (arr, idx) in self.scan_cols.items():
@@ -1470,9 +1473,16 @@ def merge_code(q, K):
         L.append("            SDQL_LAUNCH(sdqlrt::k_owner_encode, og, sdqlrt::kBlock, 0, st, c.%s.rep, own_%s, c.%s.cap, a->rank);" % (t.name, t.name, t.name))
         L.append("            if (a->merge(a->merge_ctx, %s, (unsigned long long)c.%s.cap, SDQLB200_MIN_I32)) return sdqlhost::fail(SDQLB200_E_ARG, \"merge callback failed\");" % (off % ("own_%s" % t.name), t.name))
         L.append("            SDQL_LAUNCH(sdqlrt::k_owner_decode, og, sdqlrt::kBlock, 0, st, c.%s.rep, own_%s, c.%s.cap, a->rank);" % (t.name, t.name, t.name))
-        for j, (_, ct) in enumerate(t.fields):
-            L.append("            if (a->merge(a->merge_ctx, %s, (unsigned long long)c.%s.cap, %s)) return sdqlhost::fail(SDQLB200_E_ARG, \"merge callback failed\");" %
-                     (off % ("c.%s_a%d" % (t.name, j)), t.name, "SDQLB200_SUM_F64" if ct == "f64" else "SDQLB200_SUM_I64"))
+        j = 0
+        while j < len(t.fields):  # consecutive aggregate arrays of one type are adjacent in the (zeroed) arena: one call
+            k = j
+            while k + 1 < len(t.fields) and t.fields[k + 1][1] == t.fields[j][1]:
+                k += 1
+            ct = t.fields[j][1]
+            cnt = "(unsigned long long)((c.%s_a%d + c.%s.cap) - c.%s_a%d)" % (t.name, k, t.name, t.name, j)
+            L.append("            if (a->merge(a->merge_ctx, %s, %s, %s)) return sdqlhost::fail(SDQLB200_E_ARG, \"merge callback failed\");" %
+                     (off % ("c.%s_a%d" % (t.name, j)), cnt, "SDQLB200_SUM_F64" if ct == "f64" else "SDQLB200_SUM_I64"))
+            j = k + 1
         L.append("        }")
     L.append("    }")
     return L
@@ -1663,12 +1673,23 @@ static int sdqlhost_sms() {
 }
 #endif
 
-// copy the result rows to host buffers (after the query's kernels): 8 bytes for the row count, then count x fields
+// copy the result rows to host buffers (after the query's kernels).  The row counter sits directly in front of the
+// result columns in the arena, so a small result (the common case: aggregates) is one D2H copy into a pinned staging
+// buffer and one synchronisation; large results copy the counter first, then exactly count rows per column.
 static int sdqlhost_fetch(sdqlb200_args* a, cudaStream_t st, unsigned long long* d_count, long long cap, int nf,
                           long long* const* d_cols) {
     unsigned long long cnt = 0;
-    SDQL_CUDA(cudaMemcpyAsync(&cnt, d_count, 8, cudaMemcpyDeviceToHost, st));
+    const size_t span = nf ? (size_t)((char*)(d_cols[nf - 1] + cap) - (char*)d_count) : 8;
+    static char* stage = nullptr;
+    const size_t kStage = 1 << 20;
+#ifndef SDQLB200_EMU
+    if (!stage && cudaHostAlloc((void**)&stage, kStage, cudaHostAllocDefault) != cudaSuccess) stage = nullptr;
+#endif
+    const bool small = stage && span <= kStage;
+    if (small) SDQL_CUDA(cudaMemcpyAsync(stage, d_count, span, cudaMemcpyDeviceToHost, st));
+    else SDQL_CUDA(cudaMemcpyAsync(&cnt, d_count, 8, cudaMemcpyDeviceToHost, st));
     SDQL_CUDA(cudaStreamSynchronize(st));
+    if (small) memcpy(&cnt, stage, 8);
     float ms = 0;
     cudaEventElapsedTime(&ms, sdqlhost_ev(0), sdqlhost_ev(1));
     a->device_ms = ms;
@@ -1681,9 +1702,11 @@ static int sdqlhost_fetch(sdqlb200_args* a, cudaStream_t st, unsigned long long*
     if (a->flags & SDQLB200_F_NOFETCH) return SDQLB200_OK;
     for (int j = 0; j < nf; ++j) {
         a->result.cols[j] = (int64_t*)malloc((cnt ? cnt : 1) * 8);
-        if (cnt) SDQL_CUDA(cudaMemcpyAsync(a->result.cols[j], d_cols[j], cnt * 8, cudaMemcpyDeviceToHost, st));
+        if (!cnt) continue;
+        if (small) memcpy(a->result.cols[j], stage + ((char*)d_cols[j] - (char*)d_count), cnt * 8);
+        else SDQL_CUDA(cudaMemcpyAsync(a->result.cols[j], d_cols[j], cnt * 8, cudaMemcpyDeviceToHost, st));
     }
-    SDQL_CUDA(cudaStreamSynchronize(st));
+    if (!small) SDQL_CUDA(cudaStreamSynchronize(st));
     return SDQLB200_OK;
 }
 
