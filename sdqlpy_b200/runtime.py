@@ -274,16 +274,29 @@ def host_strings(src, rows):
 # results (fastd-compatible surface)
 # ---------------------------------------------------------------------------------------------
 class ResultSet:
-    """set of records returned by a query: the surface of the reference's fastd wrapper (fastd.py:31-51)."""
+    """set of records returned by a query: the surface of the reference's fastd wrapper (fastd.py:31-51).
+    Like the reference's FastDict it stays in native (columnar) form; Python tuples / records are only built when
+    asked for (tuples(), to_dict(), print), with string fields gathered from the host columns by row id."""
 
-    def __init__(self, names, rows):
-        self.names, self.rows = list(names), rows
+    def __init__(self, names, rows=None, lazy=None):
+        self.names, self._rows, self._lazy = list(names), rows, lazy
+
+    @property
+    def rows(self):
+        if self._rows is None:
+            cols, decoders = self._lazy
+            out = [d(c) for d, c in zip(decoders, cols)]
+            self._rows = list(dict.fromkeys(zip(*out))) if out and len(cols[0]) else []
+            self._lazy = None
+        return self._rows
 
     def size(self):
-        return len(self.rows)
+        if self._rows is None:
+            cols, _ = self._lazy
+            return int(len(cols[0])) if cols else 0
+        return len(self._rows)
 
-    def __len__(self):
-        return len(self.rows)
+    __len__ = size
 
     def to_dict(self):
         from .sdql_lib import record, sr_dict
@@ -365,10 +378,10 @@ class CompiledModule:
             mn, mx, flags = c.min, c.max, 0
             arg, cname, rep = q["inputs"][i]
             if DIST is not None and DIST.world > 1 and arg in DIST.partitioned:
-                if rep == "i32":
-                    mn, mx = DIST.global_range((name, i), mn, mx)
                 if cname in DIST.partkeys:
-                    flags = 1
+                    flags = 1  # tables keyed by the partitioning column stay rank-local: local value range suffices
+                elif rep == "i32":
+                    mn, mx = DIST.global_range((name, i), mn, mx)
             carr[i] = Col(c.ptr, c.rows, mn, mx, c.width, KIND_ID[c.kind], flags, 0)
         if DIST is not None and DIST.world > 1:
             a.part_mask = sum(1 << i for i, g in enumerate(q["args"]) if g in DIST.partitioned)
@@ -433,12 +446,18 @@ class CompiledModule:
         info.device_ms, info.launches, info.tier = float(a.device_ms), int(a.launches), int(a.tier)
         info.workspace_bytes, info.h2d_bytes, info.d2h_bytes, info.rows = int(a.workspace_needed), STORE.h2d_bytes - h2d0, 8 + n * nf * 8, n
         self.last = info
-        res = self.box(q, db, cols, n)
-        if int(a.result_partial) and DIST is not None and DIST.world > 1 and isinstance(res, ResultSet):
-            parts = [None] * DIST.world  # result rows are this rank's share: concatenate the ranks
-            DIST.dist.all_gather_object(parts, res.rows, group=DIST.group)
-            res = ResultSet(res.names, list(dict.fromkeys(r for p in parts for r in p)))
-        return res
+        if int(a.result_partial) and DIST is not None and DIST.world > 1 and q["result_kind"] == "rows":
+            # every group was emitted by exactly one (owner) rank: concatenate the ranks' columns.  String fields that
+            # reference rows of a partitioned relation are decoded before they leave the rank that owns those rows.
+            for j, (fname, fk) in enumerate(q["result"]):
+                if fk.startswith("str:ref:") and fk.split(":")[2] in DIST.partitioned:
+                    raise NotImplementedError("string result field from a partitioned relation across GPUs")
+            parts = [None] * DIST.world
+            DIST.dist.all_gather_object(parts, cols, group=DIST.group)
+            cols = [np.concatenate([p[j] for p in parts]) for j in range(nf)]
+            n = len(cols[0]) if cols else 0
+            info.rows = n
+        return self.box(q, db, cols, n)
 
     def box(self, q, db, cols, n):
         kind = q["result_kind"]
@@ -447,34 +466,34 @@ class CompiledModule:
         if kind == "i64":
             return int(cols[0][0])
         argpos = {a: i for i, a in enumerate(q["args"])}
-        out, names = [], []
+        decoders, names = [], []
         for (fname, fk), c in zip(q["result"], cols):
             names.append(fname)
             if fk == "f64":
-                out.append(c.view(np.float64).tolist())
+                decoders.append(lambda c: c.view(np.float64).tolist())
             elif fk == "i64":
-                out.append(c.tolist())
+                decoders.append(lambda c: c.tolist())
             elif fk == "bool":
-                out.append([bool(x) for x in c])
+                decoders.append(lambda c: [bool(x) for x in c])
             elif fk.startswith("str:ref:"):
                 _, _, arg, col = fk.split(":")
                 cn = [x for x, _ in q["schemas"][arg]]
-                out.append(host_strings(db[argpos[arg]][cn.index(col)], c))
+                src = db[argpos[arg]][cn.index(col)]
+                decoders.append(lambda c, src=src: host_strings(src, c))
             elif fk.startswith("str:code:"):
                 _, _, arg, col = fk.split(":")
                 cn = [x for x, _ in q["schemas"][arg]]
                 kindc = dict((x, k) for x, k in q["schemas"][arg])[col]
                 d = STORE.get(db[argpos[arg]][cn.index(col)], "code", kindc[1]).dictionary
-                out.append([d[i] for i in c])
+                decoders.append(lambda c, d=d: [d[i] for i in c])
             elif fk.startswith("str:pack:"):
                 nb = int(fk.split(":")[2])
-                out.append([int(v).to_bytes(nb, "big").split(b"\0", 1)[0].decode("latin1") for v in c])
+                decoders.append(lambda c, nb=nb: [int(v).to_bytes(nb, "big").split(b"\0", 1)[0].decode("latin1") for v in c])
             elif fk.startswith("str:const:"):
-                out.append([fk[len("str:const:"):]] * n)
+                decoders.append(lambda c, v=fk[len("str:const:"):]: [v] * len(c))
             else:
                 raise ValueError(fk)
-        rows = list(dict.fromkeys(zip(*out))) if out and n else []
-        return ResultSet(names, rows)
+        return ResultSet(names, None, (cols, decoders))
 
 
 _modules = {}
