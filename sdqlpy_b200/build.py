@@ -91,6 +91,18 @@ def nvcc(cu, so, verbose=False):
     return so
 
 
+def compile_wire(force=False):
+    """csrc/sdqlb200_wire.cu -> sdqlpy_b200/_build/libsdqlb200_wire.so (column wire-format decoders, sm_100a)."""
+    src = os.path.join(CSRC, "sdqlb200_wire.cu")
+    out_dir = os.path.join(PKG, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libsdqlb200_wire.so")
+    deps = [src, os.path.join(INC, "sdqlb200_wire.h"), os.path.join(INC, "sdqlb200.h")]
+    if not force and os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps):
+        return so
+    return nvcc(src, so)
+
+
 def compile_file(script_path, force=False, verbose=False):
     """generate + build the module of one query script; returns the .so path."""
     cu, so = out_paths(script_path)

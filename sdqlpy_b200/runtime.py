@@ -73,6 +73,11 @@ class CudaBackend:
         d.copy_(t, non_blocking=t.is_pinned())
         return d.data_ptr(), d
 
+    def upload_packed(self, packed):
+        """wire.Packed -> (device pointer of the expanded column, holder, bytes that crossed the link)."""
+        from . import wire
+        return wire.upload_decoded(packed, self)
+
     def pinned_like(self, arr):
         """copy of a numpy array in page-locked host memory (numpy view, backing tensor)."""
         t = self.torch.empty(arr.shape, dtype=self.torch.from_numpy(arr[:0]).dtype, pin_memory=True)
@@ -212,10 +217,18 @@ class ColumnStore:
         k = (self.key(src), rep, width)
         if self.enabled and k in self.cache:
             return self.cache[k][0]
-        img, mn, mx, w, d = _encode(src, rep, width)
-        ptr, holder = backend().upload(img)
-        self.h2d_bytes += img.nbytes
-        col = DeviceColumn(rep, ptr, holder, img.shape[0], mn, mx, w, d, img.nbytes)
+        packed = getattr(src, "wire", None)
+        if packed is not None and packed.rep == rep and packed.rows == len(src.data):
+            # the column crosses the link in its packed form and is expanded on the device (csrc/sdqlb200_wire.cu)
+            ptr, holder, h2d = backend().upload_packed(packed)
+            self.h2d_bytes += h2d
+            col = DeviceColumn(rep, ptr, holder, packed.rows, packed.min, packed.max, 4 if rep == "i32" else 8, None,
+                               packed.rows * (4 if rep == "i32" else 8))
+        else:
+            img, mn, mx, w, d = _encode(src, rep, width)
+            ptr, holder = backend().upload(img)
+            self.h2d_bytes += img.nbytes
+            col = DeviceColumn(rep, ptr, holder, img.shape[0], mn, mx, w, d, img.nbytes)
         if self.enabled:
             self.cache[k] = (col, src)  # keep the host object alive so the identity key stays valid
         return col

@@ -203,10 +203,11 @@ def _put(mat, rows, start, word):
 
 class Column:
     """One generated column in compact form.  kind: 'i32' | 'i64' | 'f64' | 'code' | 'bytes'."""
-    __slots__ = ("name", "kind", "data", "dictionary", "width")
+    __slots__ = ("name", "kind", "data", "dictionary", "width", "wire")
 
     def __init__(self, name, kind, data, dictionary=None, width=None):
         self.name, self.kind, self.data, self.dictionary, self.width = name, kind, data, dictionary, width
+        self.wire = None  # optional lossless packed image for the host -> device link (sdqlpy_b200.wire.Packed)
 
     def to_ref(self):
         if self.kind in ("i32", "i64"):

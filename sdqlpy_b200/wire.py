@@ -1,0 +1,176 @@
+"""Column wire formats: lossless packed host images of columns for the host -> device link, expanded on the device by
+csrc/sdqlb200_wire.cu (C ABI: include/sdqlb200_wire.h).
+
+The reference keeps every column as int64 / float64 / UCS4 in host memory (read_csv, sdql_lib.py:83-97) and the
+generated module reads those buffers in place (sdql_compiler.py:644-668).  A B200 reads its columns from HBM, so
+they have to cross PCIe once per upload; packing is done once per column at load time (the moment the reference
+spends in read_csv), never per query.  Every packed form is verified bit for bit against the column it encodes --
+when no packed form is exact the column travels in its resident form.
+
+    dict8 / dict16   value -> code into a sorted dictionary of the distinct values (quantities, discounts, taxes,
+                     dates, small integer domains)
+    fixed32          decimal(.,2) money: int32 hundredths, decoded as (double)v / 100.0 -- IEEE division gives exactly
+                     the double a decimal parser produces for the same digits
+"""
+import ctypes
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+WIRE_SO = os.path.join(PKG, "_build", "libsdqlb200_wire.so")
+
+DICT8_F64, DICT16_F64, DICT8_I32, DICT16_I32, FIXED32_F64 = range(5)
+KIND_NAMES = ["dict8_f64", "dict16_f64", "dict8_i32", "dict16_i32", "fixed32_f64"]
+SRC_WIDTH = [1, 2, 1, 2, 4]
+DST_DTYPE = [np.float64, np.float64, np.int32, np.int32, np.float64]
+SAMPLE = 1 << 20
+
+
+class Packed:
+    """one packed column: ``codes`` (the image that crosses the link), ``table`` (dictionary, tiny) or ``scale``."""
+    __slots__ = ("kind", "codes", "table", "scale", "rows", "rep", "min", "max", "_dev_table", "_pin")
+
+    def __init__(self, kind, codes, table=None, scale=0.0, rep="f64", mn=0, mx=0):
+        self.kind, self.codes, self.table, self.scale, self.rows, self.rep = kind, codes, table, float(scale), len(codes), rep
+        self.min, self.max = mn, mx
+        self._dev_table, self._pin = None, None
+
+    @property
+    def nbytes(self):
+        return self.codes.nbytes + (self.table.nbytes if self.table is not None else 0)
+
+    def pin(self, be):
+        """move the packed image to page-locked host memory (asynchronous uploads)."""
+        if self._pin is None:
+            raw, self._pin = be.pinned_like(self.codes.view(np.uint8))
+            self.codes = raw.view(self.codes.dtype)
+        return self
+
+    def decode_host(self):
+        """numpy restatement of the device kernels (tests / oracle side only)."""
+        if self.kind == FIXED32_F64:
+            return self.codes.astype(np.float64) / self.scale
+        return self.table[self.codes]
+
+
+def _bits(a):
+    return a.view(np.int64) if a.dtype == np.float64 else a
+
+
+def _try_dict(a, limit=65536):
+    """-> (codes, table) with table[codes] == a bit for bit, or None."""
+    n = len(a)
+    if n == 0:
+        return None
+    tab = np.unique(a[:SAMPLE])
+    for _ in range(2):
+        if len(tab) > limit:
+            return None
+        codes = np.searchsorted(tab, a)
+        np.minimum(codes, len(tab) - 1, out=codes)
+        bad = _bits(tab[codes]) != _bits(a)
+        if not bad.any():
+            ct = np.uint8 if len(tab) <= 256 else np.uint16
+            return codes.astype(ct), tab
+        extra = np.unique(a[bad])
+        if len(extra) + len(tab) > limit or (a.dtype == np.float64 and np.isnan(extra).any()):
+            return None
+        tab = np.unique(np.concatenate([tab, extra]))
+        # -0.0 / +0.0 collapse in np.unique: the bitwise check above rejects such a column on the second pass
+    return None
+
+
+def _try_fixed32(a, scale=100.0):
+    if a.dtype != np.float64 or len(a) == 0:
+        return None
+    with np.errstate(invalid="ignore", over="ignore"):
+        v = np.rint(a * scale)
+        if not np.isfinite(v).all() or np.abs(v).max() >= 2**31:
+            return None
+        c = v.astype(np.int32)
+        if (_bits(c.astype(np.float64) / scale) != _bits(a)).any():
+            return None
+    return c
+
+
+def pack(arr, rep):
+    """host column in its resident form (int32 / float64 numpy array) -> Packed, or None when it should travel as is."""
+    a = np.ascontiguousarray(arr)
+    want = {"i32": np.int32, "f64": np.float64}.get(rep)
+    if want is None or a.dtype != want or len(a) < 1024:
+        return None
+    mn = mx = 0
+    if rep == "i32":
+        mn, mx = int(a.min()), int(a.max())
+    d = _try_dict(a)
+    if d is not None:
+        codes, tab = d
+        wide = codes.dtype == np.uint16
+        kind = (DICT16_F64 if wide else DICT8_F64) if rep == "f64" else (DICT16_I32 if wide else DICT8_I32)
+        return Packed(kind, codes, np.ascontiguousarray(tab), 0.0, rep, mn, mx)
+    if rep == "f64":
+        c = _try_fixed32(a)
+        if c is not None:
+            return Packed(FIXED32_F64, c, None, 100.0, rep)
+    return None
+
+
+def pack_column(col):
+    """attach the packed image to a tpch.gen.Column (no-op for kinds that are already narrow: codes, bytes)."""
+    if getattr(col, "wire", None) is None and col.kind in ("i32", "f64"):
+        col.wire = pack(col.data, col.kind)
+    return col
+
+
+def pack_db(db):
+    """pack every column of a db (list of per-relation column lists) once, at load time."""
+    for rel in db:
+        for c in rel:
+            if c is not None and hasattr(c, "kind") and hasattr(c, "wire"):
+                pack_column(c)
+    return db
+
+
+# ---------------------------------------------------------------------------------------------
+# device side
+# ---------------------------------------------------------------------------------------------
+_lib = None
+
+
+def lib():
+    """libsdqlb200_wire.so; raises if it was not built (no CPU fallback on the product path)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(WIRE_SO):
+            raise ImportError("%s not found (run __graft_entry__.build() / sdqlpy_b200.build.compile_wire())" % WIRE_SO)
+        L = ctypes.CDLL(WIRE_SO)
+        L.sdqlb200_wire_decode.argtypes = [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                           ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
+        L.sdqlb200_wire_decode.restype = ctypes.c_int
+        L.sdqlb200_wire_last_error.restype = ctypes.c_char_p
+        L.sdqlb200_wire_src_width.argtypes = [ctypes.c_int32]
+        L.sdqlb200_wire_dst_width.argtypes = [ctypes.c_int32]
+        _lib = L
+    return _lib
+
+
+def upload_decoded(p, be):
+    """Packed -> (device pointer, holder, bytes that crossed the link): upload the packed image on the current stream
+    and expand it there."""
+    L = lib()
+    h2d = p.codes.nbytes
+    src_ptr, src_hold = be.upload(p.codes.view(np.uint8))
+    tab_ptr = None
+    if p.table is not None:
+        if p._dev_table is None or p._dev_table[2] is not be:
+            tp, th = be.upload(p.table)
+            p._dev_table = (tp, th, be)
+            h2d += p.table.nbytes
+        tab_ptr = p._dev_table[0]
+    dst_ptr, dst_hold = be.alloc(p.rows * np.dtype(DST_DTYPE[p.kind]).itemsize)
+    rc = L.sdqlb200_wire_decode(p.kind, src_ptr, dst_ptr, p.rows, tab_ptr, p.scale, be.stream())
+    if rc != 0:
+        raise RuntimeError("sdqlb200_wire_decode failed (%d): %s" % (rc, L.sdqlb200_wire_last_error().decode()))
+    # src_hold is dropped here: the caching allocator reuses it in stream order, after the decode kernel
+    return dst_ptr, dst_hold, h2d

@@ -28,6 +28,11 @@ class EmuBackend:
             a = np.zeros(16, dtype=np.uint8)
         return a.ctypes.data, a
 
+    def upload_packed(self, packed):
+        # the emulation "device" is host memory: expand with the numpy restatement of the decode kernels
+        a = np.ascontiguousarray(packed.decode_host())
+        return a.ctypes.data, a, packed.codes.nbytes
+
     def alloc(self, nbytes):
         a = np.zeros(max(int(nbytes), 256), dtype=np.uint8)
         return a.ctypes.data, a
