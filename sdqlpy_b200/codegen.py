@@ -36,10 +36,15 @@ class CodegenError(Exception):
     pass
 
 
-# scan-loop latency hiding: "reg" = double-buffer the next row group in registers; "l2" = single register buffer
-# plus prefetch.global.L2 of the group PF_DIST iterations ahead (fewer registers -> more resident warps)
-PIPELINE = os.environ.get("SDQLB200_PIPELINE", "auto")  # auto: l2 for shared-memory-tiered or wide (>= 6 column) scans
+# scan-loop latency hiding:
+#   "tma" = bulk-async (TMA engine) copies of whole column tiles into a multi-stage shared-memory ring tracked by
+#           mbarriers: bytes in flight = stages x tile, no registers held by outstanding loads
+#   "reg" = 128-bit LDGs, the next row group double-buffered in registers
+#   "l2"  = 128-bit LDGs, single register buffer plus prefetch.global.L2 of the group PF_DIST iterations ahead
+PIPELINE = os.environ.get("SDQLB200_PIPELINE", "auto")  # auto: see Kernel.pipe_mode
 PF_DIST = int(os.environ.get("SDQLB200_PF_DIST", "2"))
+RING_ROWS_PER_THREAD = int(os.environ.get("SDQLB200_RING_ROWS", "0"))  # 0 = per kernel (Kernel.ring_rows)
+RING_MAX_ROW_BYTES = 100     # wider scans cannot keep two stages in 227 KB of shared memory: they use LDGs
 
 
 # =============================================================================================
@@ -302,6 +307,26 @@ class Kernel:
     def emit(self, s):
         self.body.append("    " * self.depth + s)
 
+    def ring_rows(self):
+        """rows per thread per tile (tile = kBlock x rows): wide scans use smaller tiles so that two CTAs per SM can
+        each keep several stages in flight and the per-thread row buffer stays small."""
+        if RING_ROWS_PER_THREAD:
+            return RING_ROWS_PER_THREAD
+        row_bytes = sum({"i32": 4, "f64": 8, "code": 1}[rep] for (_, rep) in self.scan_cols)
+        return 4 if row_bytes <= 24 else 2
+
+    def pipe_mode(self):
+        if self.src[0] != "rel" or not self.scan_cols:
+            return None
+        pipe = PIPELINE
+        if pipe == "auto":
+            pipe = "tma"
+        if pipe == "legacy":
+            pipe = "l2" if (self.tiered or len(self.scan_cols) >= 6) else "reg"
+        if pipe == "tma" and sum({"i32": 4, "f64": 8, "code": 4}[rep] for (_, rep) in self.scan_cols) > RING_MAX_ROW_BYTES:
+            pipe = "l2"
+        return pipe
+
     def tmp(self, p="t"):
         self.ntmp += 1
         return "%s%d" % (p, self.ntmp)
@@ -345,8 +370,12 @@ class Kernel:
         tmpl = "template <int TIER>\n" if self.tiered else ""
         L.append("%s__global__ void __launch_bounds__(sdqlrt::kBlock) %s(const __grid_constant__ %s_ctx c) {" %
                  (tmpl, self.name, q.name))
+        if self.tiered or self.pipe_mode() == "tma":
+            L.append("    SDQL_EXTERN_SMEM(sm);")
         L += ["    " + s for s in self.pre]
-        if self.src[0] == "rel":
+        if self.src[0] == "rel" and self.pipe_mode() == "tma":
+            L += self.render_ring()
+        elif self.src[0] == "rel":
             # software-pipelined streaming loop: the next group's column loads are issued before the current
             # group is processed, so every thread keeps two groups (2 x 4 rows x all columns) in flight
             ety = {"i32": "int", "f64": "double", "code": "int"}
@@ -380,9 +409,7 @@ class Kernel:
             L.append("    const long long ngrp = (n + 3) >> 2;")
             L.append("    const long long gstride = (long long)gridDim.x * blockDim.x;")
             L.append("    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
-            pipe = PIPELINE
-            if pipe == "auto":
-                pipe = "l2" if (self.tiered or len(self.scan_cols) >= 6) else "reg"
+            pipe = self.pipe_mode() or "reg"
             if pipe == "reg":
                 for (col, rep), (arr, idx) in self.scan_cols.items():
                     L.append("    %s %s[4], %s[4];" % (ety[rep], arr, "q_" + arr[2:]))
@@ -436,6 +463,106 @@ class Kernel:
         L += ["    " + s for s in self.post]
         L.append("}")
         return "\n".join(L)
+
+
+def _render_ring(self):
+    """rel-scan loop over a shared-memory ring of column tiles filled by bulk-async (TMA) copies.
+
+    tile = blockDim.x * R rows; thread t of the CTA owns rows t, t + blockDim.x, ... of a tile (conflict-free shared
+    memory reads).  CTA b processes tiles b, b + gridDim.x, ...; thread 0 keeps S tiles in flight: it arms full[s]
+    with the stage's byte count, issues one bulk copy per scanned column, and refills a stage as soon as every warp
+    has arrived on empty[s] (the warps arrive right after copying their rows to registers, before computing).
+    The last, partial tile of the relation is read with plain guarded loads.  Under SDQLB200_EMU (tests) every tile
+    takes that path."""
+    R = self.ring_rows()
+    ety = {"i32": "int", "f64": "double", "code": "int"}
+    cols = list(self.scan_cols.items())
+    L = []
+    L.append("    const long long n = c.n_%s;" % self.src[1])
+    L.append("    const int TILE = (int)blockDim.x * %d;" % R)
+    L.append("    const long long ntile = (n + TILE - 1) / TILE;")
+    for (col, rep), (arr, idx) in cols:
+        L.append("    %s %s[%d];" % (ety[rep], arr, R))
+    L.append("#ifndef SDQLB200_EMU")
+    L.append("    const long long nfull = n / TILE;")
+    L.append("    unsigned char* const ring = (unsigned char*)sm + c.%s_ro;" % self.name)
+    L.append("    const int S = c.%s_rs;" % self.name)
+    L.append("    unsigned long long* const full = (unsigned long long*)ring;")
+    L.append("    unsigned long long* const empty = full + 8;")
+    L.append("    unsigned char* const stage0 = ring + 128;")
+    off = "0u"
+    for j, ((col, rep), (arr, idx)) in enumerate(cols):
+        w = {"i32": "4u", "f64": "8u", "code": "(unsigned)c.in%d_w" % idx}[rep]
+        L.append("    const unsigned o%d = %s, b%d = %s * (unsigned)TILE;" % (j, off, j, w))
+        off = "o%d + b%d" % (j, j)
+    L.append("    const unsigned sbytes = %s;" % off)
+    L.append("    const unsigned sstride = (sbytes + 127u) & ~127u;")
+    L.append("    auto issue = [&](int s, long long k) {")
+    L.append("        unsigned char* const st = stage0 + (size_t)s * sstride;")
+    L.append("        sdqlrt::mbar_expect_tx(full + s, sbytes);")
+    for j, ((col, rep), (arr, idx)) in enumerate(cols):
+        if rep == "code":
+            L.append("        sdqlrt::bulk_g2s(st + o%d, (const unsigned char*)c.in%d + k * TILE * c.in%d_w, b%d, full + s);" % (j, idx, idx, j))
+        else:
+            L.append("        sdqlrt::bulk_g2s(st + o%d, c.in%d + k * TILE, b%d, full + s);" % (j, idx, j))
+    L.append("    };")
+    L.append("    if (threadIdx.x == 0) {")
+    L.append("        for (int s = 0; s < S; ++s) { sdqlrt::mbar_init(full + s, 1u); sdqlrt::mbar_init(empty + s, blockDim.x >> 5); }")
+    L.append("        sdqlrt::mbar_fence_init();")
+    L.append("    }")
+    L.append("    __syncthreads();")
+    L.append("    if (threadIdx.x == 0)")
+    L.append("        for (int s = 0; s < S; ++s) { const long long k = blockIdx.x + (long long)s * gridDim.x; if (k < nfull) issue(s, k); }")
+    L.append("    int rs = 0; unsigned rph = 0;  // ring stage / phase parity of the current tile")
+    L.append("#else")
+    L.append("    const long long nfull = 0;")
+    L.append("#endif")
+    L.append("    for (long long k = blockIdx.x; k < ntile; k += gridDim.x) {")
+    L.append("        const long long i0 = k * TILE + threadIdx.x;")
+    L.append("        if (k < nfull) {")
+    L.append("#ifndef SDQLB200_EMU")
+    L.append("            sdqlrt::mbar_wait(full + rs, rph);")
+    L.append("            const unsigned char* const st = stage0 + (size_t)rs * sstride;")
+    L.append("#pragma unroll")
+    L.append("            for (int u = 0; u < %d; ++u) {" % R)
+    L.append("                const int e = u * (int)blockDim.x + (int)threadIdx.x;")
+    for j, ((col, rep), (arr, idx)) in enumerate(cols):
+        if rep == "code":
+            L.append("                %s[u] = c.in%d_w == 1 ? (int)(st + o%d)[e] : ((const int*)(st + o%d))[e];" % (arr, idx, j, j))
+        else:
+            L.append("                %s[u] = ((const %s*)(st + o%d))[e];" % (arr, ety[rep], j))
+    L.append("            }")
+    L.append("            __syncwarp();")
+    L.append("            if ((threadIdx.x & 31) == 0) sdqlrt::mbar_arrive(empty + rs);")
+    L.append("            if (threadIdx.x == 0) {")
+    L.append("                const long long kn = k + (long long)S * gridDim.x;")
+    L.append("                if (kn < nfull) { sdqlrt::mbar_wait(empty + rs, rph); issue(rs, kn); }")
+    L.append("            }")
+    L.append("            if (++rs == S) { rs = 0; rph ^= 1u; }")
+    L.append("#endif")
+    L.append("        } else {")
+    L.append("            for (int u = 0; u < %d; ++u) {" % R)
+    L.append("                const long long iu = i0 + (long long)u * blockDim.x;")
+    L.append("                const long long ii = iu < n ? iu : n - 1;")
+    for (col, rep), (arr, idx) in cols:
+        if rep == "code":
+            L.append("                %s[u] = sdqlrt::ld1_code(c.in%d, ii, c.in%d_w);" % (arr, idx, idx))
+        else:
+            L.append("                %s[u] = sdqlrt::ld1(c.in%d + ii);" % (arr, idx))
+    L.append("            }")
+    L.append("        }")
+    L.append("#pragma unroll")
+    L.append("        for (int u = 0; u < %d; ++u) {" % R)
+    L.append("            const long long i = i0 + (long long)u * blockDim.x;")
+    L.append("            if (i < n) {")
+    L += ["                " + x for x in self.body]
+    L.append("            }")
+    L.append("        }")
+    L.append("    }")
+    return L
+
+
+Kernel.render_ring = _render_ring
 
 
 # =============================================================================================
@@ -626,15 +753,13 @@ class GroupSink(KeyedSink):
         nf = len(t.fields)
         vals = [cast_to(x, ct) for (n, x), (_, ct) in zip(items, t.fields)]
         if self.tiered:
+            # TIER 0: accumulators of every (slot, field) cell live in registers; the row's slot is matched against the
+            # statically unrolled slot index (predicated adds, no shared-memory traffic, no atomics)
             K.emit("if (TIER == 0) {")
-            K.emit("    const int sb = (int)%s * %d * (int)blockDim.x + (int)threadIdx.x;" % (kk, nf))
-            for j, (_, ct) in enumerate(t.fields):
-                idx = "sb + %d * (int)blockDim.x" % j
-                if ct == "f64":
-                    K.emit("    sm[%s] = __double_as_longlong(__longlong_as_double(sm[%s]) + %s);" % (idx, idx, vals[j]))
-                else:
-                    K.emit("    sm[%s] += (unsigned long long)(%s);" % (idx, vals[j]))
-            K.emit("    smrep[(int)%s * (int)blockDim.x + (int)threadIdx.x] = (int)%s;" % (kk, K.scan_var))
+            for sl_ in range(self.rcap):  # unrolled here (scalar accumulators: nothing can end up in local memory)
+                upd = " ".join("ra%d_%d += %s;" % (j, sl_, ("(unsigned long long)(%s)" % vals[j]) if ct != "f64" else vals[j])
+                               for j, (_, ct) in enumerate(t.fields))
+                K.emit("    if ((int)%s == %d) { %s rrep_%d = (int)%s; }" % (kk, sl_, upd, sl_, K.scan_var))
             K.emit("} else if (TIER == 1) {")
             K.emit("    const int sb = (int)%s * %d;" % (kk, nf))
             for j, (_, ct) in enumerate(t.fields):
@@ -681,11 +806,14 @@ class GroupSink(KeyedSink):
         K, t = self.K, self.t
         nf = len(t.fields)
         K.tiered = True
-        K.pre.append("SDQL_EXTERN_SMEM(sm);")
+        self.rcap = max(1, min(8, 32 // nf))  # register tier: <= 8 groups and <= 32 accumulator cells per thread
+        K.rcap = self.rcap
         K.pre.append("const long long ncap = c.%s.cap;" % t.name)
-        K.pre.append("int* smrep = (int*)(sm + (TIER == 0 ? ncap * %d * blockDim.x : ncap * %d));" % (nf, nf))
-        K.pre.append("if (TIER == 0) { for (long long k = 0; k < ncap * %d; ++k) sm[k * blockDim.x + threadIdx.x] = 0; "
-                     "for (long long k = 0; k < ncap; ++k) smrep[k * blockDim.x + threadIdx.x] = -1; }" % nf)
+        for j, (_, ct) in enumerate(t.fields):
+            K.pre.append("%s %s;" % ("double" if ct == "f64" else "unsigned long long",
+                                     ", ".join("ra%d_%d = 0" % (j, sl_) for sl_ in range(self.rcap))))
+        K.pre.append("int %s;" % ", ".join("rrep_%d = -1" % sl_ for sl_ in range(self.rcap)))
+        K.pre.append("int* smrep = (int*)(sm + ncap * %d);" % nf)
         K.pre.append("if (TIER == 1) { for (long long k = threadIdx.x; k < ncap * %d; k += blockDim.x) sm[k] = 0; "
                      "for (long long k = threadIdx.x; k < ncap; k += blockDim.x) smrep[k] = -1; __syncthreads(); }" % nf)
         K.smem_nf = nf
@@ -697,20 +825,20 @@ class GroupSink(KeyedSink):
             nf = len(t.fields)
             P = K.post
             P.append("if (TIER == 0) {")
-            P.append("    for (long long k = 0; k < ncap; ++k) {")
-            P.append("        int r = sdqlrt::block_max(smrep[k * blockDim.x + threadIdx.x]);")
-            for j, (_, ct) in enumerate(t.fields):
-                idx = "sm[(k * %d + %d) * blockDim.x + threadIdx.x]" % (nf, j)
-                if ct == "f64":
-                    P.append("        double v%d = sdqlrt::block_sum(__longlong_as_double(%s));" % (j, idx))
-                else:
-                    P.append("        long long v%d = sdqlrt::block_sum((long long)%s);" % (j, idx))
-            P.append("        if (threadIdx.x == 0 && r >= 0) {")
-            P.append("            atomicMax(c.%s.rep + k, r);" % t.name)
-            for j, (_, ct) in enumerate(t.fields):
-                P.append("            sdqlrt::red_add(c.%s_a%d + k, v%d);" % (t.name, j, j))
-            P.append("        }")
-            P.append("    }")
+            for sl_ in range(self.rcap):
+                P.append("    if (%d < ncap) {" % sl_)
+                P.append("        const int r = sdqlrt::block_max(rrep_%d);" % sl_)
+                for j, (_, ct) in enumerate(t.fields):
+                    if ct == "f64":
+                        P.append("        const double v%d = sdqlrt::block_sum(ra%d_%d);" % (j, j, sl_))
+                    else:
+                        P.append("        const long long v%d = sdqlrt::block_sum((long long)ra%d_%d);" % (j, j, sl_))
+                P.append("        if (threadIdx.x == 0 && r >= 0) {")
+                P.append("            atomicMax(c.%s.rep + %d, r);" % (t.name, sl_))
+                for j, (_, ct) in enumerate(t.fields):
+                    P.append("            sdqlrt::red_add(c.%s_a%d + %d, v%d);" % (t.name, j, sl_, j))
+                P.append("        }")
+                P.append("    }")
             P.append("} else if (TIER == 1) {")
             P.append("    __syncthreads();")
             P.append("    for (long long k = threadIdx.x; k < ncap; k += blockDim.x) {")
@@ -1510,6 +1638,9 @@ def render_query(q):
         L.append("    sdqlrt::Tbl %s; long long %s_mn[%d], %s_rng[%d], %s_mul[%d];" % (t.name, t.name, P, t.name, P, t.name, P))
         for j, (_, ct) in enumerate(t.fields):
             L.append("    %s* %s_a%d;" % (CT[ct], t.name, j))
+    for K in q.kernels:
+        if K.pipe_mode() == "tma":
+            L.append("    unsigned %s_ro; int %s_rs;  // column tile ring: byte offset in dynamic shared memory, stages" % (K.name, K.name))
     L.append("    double* sc; double* part; unsigned* cnt;")
     for i in range(len(q.npart)):
         L.append("    long long part_off%d;" % i)
@@ -1563,7 +1694,7 @@ def render_query(q):
     for t in q.tables:
         L.append("    int* own_%s = a->merge ? ar.alloc<int>(c.%s.cap) : nullptr;" % (t.name, t.name))
     L.append("    c.sc = ar.alloc<double>(%d); c.cnt = ar.alloc<unsigned>(%d);" % (max(1, q.nsc), max(1, q.ncnt)))
-    # grids
+    # launch plans: aggregation tier, shared memory (tier table + column tile ring), resident CTAs per SM, grid
     for K in q.kernels:
         if K.src[0] == "rel":
             L.append("    const long long w_%s = (c.n_%s + 3) / 4;" % (K.name, K.src[1]))
@@ -1571,7 +1702,35 @@ def render_query(q):
             L.append("    const long long w_%s = c.%s.cap;" % (K.name, K.src[1].name))
         else:
             L.append("    const long long w_%s = 1;" % K.name)
-        L.append("    int g_%s = sdqlhost::grid_for(w_%s, 8, sms);" % (K.name, K.name))
+        ring = K.pipe_mode() == "tma"
+        L.append("    int g_%s = 1, tier_%s = 2; size_t sm_%s = 0;" % (K.name, K.name, K.name))
+        L.append("    {")
+        if K.tiered:
+            nf, tn = K.smem_nf, K.smem_tbl
+            L.append("        const long long cap = c.%s.cap;" % tn)
+            L.append("        if (c.%s.direct && cap <= %d) tier_%s = 0;" % (tn, K.rcap, K.name))
+            L.append("        else if (c.%s.direct && cap * (%d * 8 + 4) <= 65536) { tier_%s = 1; sm_%s = (size_t)cap * (%d * 8 + 4); }" %
+                     (tn, nf, K.name, K.name, nf))
+            fn = "(tier_%s == 0 ? (const void*)%s<0> : tier_%s == 1 ? (const void*)%s<1> : (const void*)%s<2>)" % (
+                K.name, K.name, K.name, K.name, K.name)
+        else:
+            fn = "(const void*)%s" % K.name
+        if ring:
+            widths = " + ".join({"i32": "4", "f64": "8", "code": "(size_t)a->cols[%d].width" % idx}[rep]
+                                for (col, rep), (arr, idx) in K.scan_cols.items())
+            L.append("        sdqlhost::RingPlan rp;")
+            L.append("        if (!sdqlhost::plan_ring(sm_%s, (%s) * (size_t)(sdqlrt::kBlock * %d), &rp))" % (K.name, widths, K.ring_rows()))
+            L.append("            return sdqlhost::fail(SDQLB200_E_ARG, \"%s: scan too wide for the shared-memory column ring\");" % K.name)
+            L.append("        c.%s_ro = rp.ring_off; c.%s_rs = rp.stages; sm_%s = rp.smem;" % (K.name, K.name, K.name))
+            for (col, rep), (arr, idx) in K.scan_cols.items():
+                L.append("        if ((size_t)a->cols[%d].data & 15) return sdqlhost::fail(SDQLB200_E_ARG, \"%s: column %s is not 16-byte aligned\");" % (idx, K.name, col))
+        L.append("        const int nb = sdqlhost_occupancy(%s, sm_%s);" % (fn, K.name))
+        if ring:
+            L.append("        g_%s = sdqlhost::grid_for_tiles((c.n_%s + sdqlrt::kBlock * %d - 1) / (sdqlrt::kBlock * %d), nb, sms);" %
+                     (K.name, K.src[1], K.ring_rows(), K.ring_rows()))
+        else:
+            L.append("        g_%s = sdqlhost::grid_for(w_%s, nb < 8 ? nb : 8, sms);" % (K.name, K.name))
+        L.append("    }")
     L.append("    long long npart = 0;")
     pi = 0
     for K in q.kernels:
@@ -1601,28 +1760,12 @@ def render_query(q):
     L.append("    if (kt) SDQL_CUDA(cudaEventRecord(sdqlhost_kev(0), st));")
     for K in q.kernels:
         if K.tiered:
-            nf, tn = K.smem_nf, K.smem_tbl
-            L.append("    {")
-            L.append("        const long long cap = c.%s.cap; int tier = 2; size_t smem = 0;" % tn)
-            L.append("        if (c.%s.direct && cap * %d <= 32) { tier = 0; smem = (size_t)cap * (%d * 8 + 4) * sdqlrt::kBlock; }" % (tn, nf, nf))
-            L.append("        else if (c.%s.direct && cap * (%d * 8 + 4) <= 65536) { tier = 1; smem = (size_t)cap * (%d * 8 + 4); }" % (tn, nf, nf))
-            L.append("        if (tier == 0) {")
-            L.append("            SDQL_CUDA(cudaFuncSetAttribute(%s<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));" % K.name)
-            L.append("            int cps = (int)(232448 / (smem + 1024)); if (cps < 1) cps = 1; if (cps > 8) cps = 8;")
-            L.append("            g_%s = sdqlhost::grid_for(w_%s, cps, sms);" % (K.name, K.name))
-            L.append("            SDQL_LAUNCH(%s<0>, g_%s, sdqlrt::kBlock, smem, st, c);" % (K.name, K.name))
-            L.append("        } else if (tier == 1) {")
-            L.append("            SDQL_CUDA(cudaFuncSetAttribute(%s<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));" % K.name)
-            L.append("            int cps = (int)(232448 / (smem + 1024)); if (cps < 1) cps = 1; if (cps > 8) cps = 8;")
-            L.append("            g_%s = sdqlhost::grid_for(w_%s, cps, sms);" % (K.name, K.name))
-            L.append("            SDQL_LAUNCH(%s<1>, g_%s, sdqlrt::kBlock, smem, st, c);" % (K.name, K.name))
-            L.append("        } else {")
-            L.append("            SDQL_LAUNCH(%s<2>, g_%s, sdqlrt::kBlock, 0, st, c);" % (K.name, K.name))
-            L.append("        }")
-            L.append("        a->tier = tier;")
-            L.append("    }")
+            L.append("    if (tier_%s == 0) SDQL_LAUNCH(%s<0>, g_%s, sdqlrt::kBlock, sm_%s, st, c);" % (K.name, K.name, K.name, K.name))
+            L.append("    else if (tier_%s == 1) SDQL_LAUNCH(%s<1>, g_%s, sdqlrt::kBlock, sm_%s, st, c);" % (K.name, K.name, K.name, K.name))
+            L.append("    else SDQL_LAUNCH(%s<2>, g_%s, sdqlrt::kBlock, sm_%s, st, c);" % (K.name, K.name, K.name))
+            L.append("    a->tier = tier_%s;" % K.name)
         else:
-            L.append("    SDQL_LAUNCH(%s, g_%s, sdqlrt::kBlock, 0, st, c);" % (K.name, K.name))
+            L.append("    SDQL_LAUNCH(%s, g_%s, sdqlrt::kBlock, sm_%s, st, c);" % (K.name, K.name, K.name))
         L.append("    SDQL_CUDA(cudaGetLastError()); ++launches;")
         L += merge_code(q, K)
         L.append("    if (kt && launches < 24) SDQL_CUDA(cudaEventRecord(sdqlhost_kev(launches), st));")
@@ -1665,6 +1808,20 @@ static bool g_kev_init = false;
 static cudaEvent_t sdqlhost_kev(int i) {
     if (!g_kev_init) { for (int k = 0; k < 25; ++k) cudaEventCreate(&g_kev[k]); g_kev_init = true; }
     return g_kev[i];
+}
+// resident CTAs per SM of `fn` at `smem` bytes of dynamic shared memory (also raises the kernel's dynamic shared
+// memory limit); cached per (kernel, size) so steady-state launches make no driver queries
+static int sdqlhost_occupancy(const void* fn, size_t smem) {
+    struct Ent { const void* fn; size_t smem; int nb; };
+    static Ent cache[512];
+    static int used = 0;
+    for (int i = 0; i < used; ++i)
+        if (cache[i].fn == fn && cache[i].smem == smem) return cache[i].nb;
+    int nb = 0;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, sdqlrt::kBlock, smem) != cudaSuccess || nb < 1) nb = 1;
+    if (used < 512) cache[used++] = Ent{fn, smem, nb};
+    return nb;
 }
 static int sdqlhost_sms() {
     static int sms = 0;

@@ -89,6 +89,41 @@ static inline bool size_table(sdqlrt::Tbl* t, int nparts, const long long* mn, c
     return true;
 }
 
+// Column tile ring (generated rel-scan kernels, "tma" pipeline): pick the number of stages and the CTAs per SM the
+// shared memory allows.  More resident CTAs (latency hiding for probes) win over deeper rings as long as every CTA
+// keeps at least two tiles in flight.  tier_smem = bytes the kernel's shared aggregation table needs in front.
+struct RingPlan {
+    int stages, ctas_per_sm;
+    unsigned ring_off;
+    size_t smem;
+};
+static inline bool plan_ring(size_t tier_smem, size_t stage_bytes, RingPlan* p) {
+    const size_t kSmemPerSM = 232448;  // 227 KB
+    const size_t off = (tier_smem + 127) & ~(size_t)127;
+    const size_t stride = (stage_bytes + 127) & ~(size_t)127;
+    if (!stride) return false;
+    for (int cps = 4; cps >= 1; --cps) {
+        const size_t per = kSmemPerSM / cps - 1536;  // 1 KB per CTA is reserved by the system, static smem < 512 B
+        if (per < off + 128 + stride) continue;
+        long long S = (long long)((per - off - 128) / stride);
+        if (S < 2 && cps > 1) continue;
+        if (S > 4) S = 4;
+        p->stages = (int)S;
+        p->ctas_per_sm = cps;
+        p->ring_off = (unsigned)off;
+        p->smem = off + 128 + (size_t)S * stride;
+        return true;
+    }
+    return false;
+}
+
+// persistent grid for tile loops: every resident CTA slot gets a CTA, never more CTAs than tiles
+static inline int grid_for_tiles(long long tiles, int ctas_per_sm, int sms) {
+    long long mx = (long long)sms * (ctas_per_sm < 1 ? 1 : ctas_per_sm);
+    if (tiles < 1) tiles = 1;
+    return (int)(tiles < mx ? tiles : mx);
+}
+
 static inline int grid_for(long long work_items, int ctas_per_sm, int sms) {
     long long g = (work_items + sdqlrt::kBlock - 1) / sdqlrt::kBlock;
     long long mx = (long long)sms * ctas_per_sm;

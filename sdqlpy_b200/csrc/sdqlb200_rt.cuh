@@ -3,6 +3,8 @@
 // vendored phmap -- SURVEY.md section 2 rows 11/12).
 //
 //   * streaming column loads    128-bit / 256-bit ld.global.nc.L1::no_allocate, 4 rows per thread per column
+//   * column tile ring          bulk-async (TMA engine) global -> shared copies of whole column tiles into a
+//                               multi-stage shared-memory ring, completion tracked by mbarriers (full / empty per stage)
 //   * Tbl                       one device dictionary: direct-indexed (dense key domain) or open-addressing hash
 //                               (atomicCAS claim, linear probing); every slot keeps a representative source index
 //   * reductions                warp-shuffle + shared-memory block reductions (fp64 / int64)
@@ -19,7 +21,7 @@
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #define SDQL_DEV __device__ __forceinline__
-#define SDQL_EXTERN_SMEM(name) extern __shared__ unsigned long long name[]
+#define SDQL_EXTERN_SMEM(name) extern __shared__ __align__(128) unsigned long long name[]
 #define SDQL_LAUNCH(kernel, grid, block, smem, stream, ...) \
     kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
 #else
@@ -59,6 +61,40 @@ SDQL_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2::evi
 SDQL_DEV void prefetch_l2(const void*) {}
 template <class T, class V> SDQL_DEV void ld4(const T* p, V (&v)[4]) { for (int k = 0; k < 4; ++k) v[k] = (V)p[k]; }
 template <class T> SDQL_DEV T ld1(const T* p) { return *p; }
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// column tile ring: cp.async.bulk (TMA engine, SASS UBLKCP) + mbarrier transaction counting.
+// One elected thread arms full[s] with the stage's byte count and issues one bulk copy per scanned column; every
+// thread waits on full[s], reads its rows from shared memory, and each warp arrives on empty[s] so the stage can be
+// refilled.  No registers are tied up by loads in flight: bytes in flight = stages x tile, independent of occupancy.
+// ---------------------------------------------------------------------------------------------
+#ifndef SDQLB200_EMU
+SDQL_DEV unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+SDQL_DEV void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+SDQL_DEV void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+SDQL_DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+SDQL_DEV void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+SDQL_DEV bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+SDQL_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned; completes on `bar` (complete_tx)
+SDQL_DEV void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
 #endif
 
 // dictionary-code columns are uint8 when the dictionary has <= 256 entries, int32 otherwise (uniform branch)

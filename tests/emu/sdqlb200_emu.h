@@ -58,5 +58,6 @@ static inline cudaEvent_t sdqlhost_kev(int) { return 0; }
 static inline int cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 static inline int cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
 static inline int sdqlhost_sms() { return 1; }
+static inline int sdqlhost_occupancy(const void*, size_t) { return 1; }
 #define cudaFuncAttributeMaxDynamicSharedMemorySize 8
 template <class F> static inline int cudaFuncSetAttribute(F, int, int) { return 0; }
