@@ -22,10 +22,24 @@ enum { SDQLB200_I32 = 0, SDQLB200_F64 = 1, SDQLB200_CODE = 2, SDQLB200_BYTES = 3
 enum { SDQLB200_OK = 0, SDQLB200_E_WORKSPACE = -1, SDQLB200_E_CUDA = -2, SDQLB200_E_ARG = -3, SDQLB200_E_NOQUERY = -4 };
 enum { SDQLB200_F_NOFETCH = 1, SDQLB200_F_KERNEL_TIMES = 2 };
 enum { SDQLB200_COL_PARTKEY = 1 };                       /* sdqlb200_col.flags: the relation is range partitioned on this column */
-enum { SDQLB200_SUM_F64 = 0, SDQLB200_SUM_I64 = 1, SDQLB200_MIN_I32 = 2 }; /* merge ops */
+enum { SDQLB200_SUM_F64 = 0, SDQLB200_SUM_I64 = 1, SDQLB200_MIN_I32 = 2, SDQLB200_MERGE_TABLE = 3 }; /* merge ops */
 /* multi-GPU: called (stream ordered) after a kernel over a partitioned relation for every partial buffer that has to
- * be combined across ranks; the callee all-reduces `count` elements at workspace + offset in place (NCCL).  */
+ * be combined across ranks.  SUM / MIN: the callee all-reduces `count` elements at workspace + offset in place (NCCL).
+ * MERGE_TABLE: `workspace_offset` carries a HOST pointer to a sdqlb200_table describing a hashed partial dictionary;
+ * the callee merges it across ranks with the sdqlb200_table_* helpers below (hash all-to-all, combine at the
+ * destination, all-gather, write back).  The reference's counterpart is the serial AddMap merge of thread-local
+ * phmap tables (map_helper.h:2-23, sdql_ir_cpp_generator_par.py:436-438). */
 typedef int (*sdqlb200_merge_fn)(void* ctx, uint64_t workspace_offset, uint64_t count, int32_t op);
+
+/* one hashed device dictionary: open addressing, linear probing, keys[slot] == ~0 means free */
+typedef struct {
+    uint64_t* keys;     /* DEVICE, cap slots                                                         */
+    int32_t* rep;       /* DEVICE, cap slots: >= 0 owned here, -1 free, -2 present but owned elsewhere */
+    int64_t cap;        /* power of two                                                              */
+    int32_t nfields;    /* aggregate fields (<= 16), one 8-byte array of cap slots each              */
+    uint32_t f64_mask;  /* bit j set: field j is fp64, else int64                                    */
+    void* agg[16];      /* DEVICE                                                                    */
+} sdqlb200_table;
 
 /* one device-resident column (replaces the borrowed numpy buffer of sdql_compiler.py:653-668) */
 typedef struct {
@@ -69,7 +83,7 @@ typedef struct {
     uint32_t part_mask;       /* bit i set: relation argument i holds only this rank's partition */
     int32_t result_partial;   /* out: 1 = result rows are this rank's share (concatenate ranks) */
     int32_t rank;             /* this process' rank among the GPUs (0 on a single GPU)          */
-    int32_t reserved2;
+    int32_t world;            /* number of ranks (0 or 1 on a single GPU)                       */
 } sdqlb200_args;
 
 int sdqlb200_num_queries(void);
@@ -81,6 +95,19 @@ const char* sdqlb200_manifest(void);
 int sdqlb200_run(const char* query, sdqlb200_args* args);
 void sdqlb200_result_free(sdqlb200_result* r);
 const char* sdqlb200_last_error(void);
+
+/* building blocks of SDQLB200_MERGE_TABLE (all stream ordered; records are 2 + nfields 8-byte words:
+ * key, owner rank, field values).  Records destined to rank d = hash(key) mod world.
+ *   count : d_counts[d] += occupied slots destined to d                      (d_counts: world zeroed uint64)
+ *   pack  : writes the records grouped by destination; d_offsets[d] = first record of d's run, d_cursor zeroed;
+ *           owner word = rank, or d_own[slot] when d_own != NULL
+ *   absorb: mode 0 -- insert / add the records into t, d_own[slot] = min(owner)  (combine at the destination)
+ *           mode 1 -- insert / overwrite fields; slots whose owner != rank (or that are new here) get rep = -2 */
+int sdqlb200_table_count(const sdqlb200_table* t, int32_t world, uint64_t* d_counts, void* stream);
+int sdqlb200_table_pack(const sdqlb200_table* t, int32_t world, int32_t rank, const int32_t* d_own,
+                        const uint64_t* d_offsets, uint64_t* d_cursor, int64_t* d_records, void* stream);
+int sdqlb200_table_absorb(const sdqlb200_table* t, const int64_t* d_records, int64_t n, int32_t mode, int32_t rank,
+                          int32_t* d_own, void* stream);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,7 @@ class CodegenError(Exception):
 #           mbarriers: bytes in flight = stages x tile, no registers held by outstanding loads
 #   "reg" = 128-bit LDGs, the next row group double-buffered in registers
 #   "l2"  = 128-bit LDGs, single register buffer plus prefetch.global.L2 of the group PF_DIST iterations ahead
-PIPELINE = os.environ.get("SDQLB200_PIPELINE", "auto")  # auto: see Kernel.pipe_mode
+PIPELINE = os.environ.get("SDQLB200_PIPELINE", "auto")  # auto | tma | reg | l2 (see Kernel.pipe_mode)
 PF_DIST = int(os.environ.get("SDQLB200_PF_DIST", "2"))
 RING_ROWS_PER_THREAD = int(os.environ.get("SDQLB200_RING_ROWS", "0"))  # 0 = per kernel (Kernel.ring_rows)
 RING_MAX_ROW_BYTES = 100     # wider scans cannot keep two stages in 227 KB of shared memory: they use LDGs
@@ -320,8 +320,8 @@ class Kernel:
             return None
         pipe = PIPELINE
         if pipe == "auto":
-            pipe = "tma"
-        if pipe == "legacy":
+            # measured on B200 at SF10 (profiles/r01_pipeline_ab.json): the LDG pipelines beat the TMA ring on every
+            # kernel class (Q1 0.43 vs 0.51 ms, Q6 0.236 vs 0.243 ms, Q18 pass 1 0.35 vs 0.45 ms), so the ring is opt-in
             pipe = "l2" if (self.tiered or len(self.scan_cols) >= 6) else "reg"
         if pipe == "tma" and sum({"i32": 4, "f64": 8, "code": 4}[rep] for (_, rep) in self.scan_cols) > RING_MAX_ROW_BYTES:
             pipe = "l2"
@@ -532,8 +532,22 @@ def _render_ring(self):
         else:
             L.append("                %s[u] = ((const %s*)(st + o%d))[e];" % (arr, ety[rep], j))
     L.append("            }")
-    L.append("            __syncwarp();")
-    L.append("            if ((threadIdx.x & 31) == 0) sdqlrt::mbar_arrive(empty + rs);")
+    # The stage may be refilled by the TMA engine as soon as every warp has arrived on empty[rs], so the arrive must
+    # not be issued before this warp's shared-memory loads have RETURNED (an LDS can sit behind global atomics /
+    # probes in the load-store queue for a long time).  Folding every loaded word into the arrive's operand makes the
+    # arrive wait on the loads' scoreboard.
+    L.append("            unsigned dep = 0;")
+    L.append("#pragma unroll")
+    L.append("            for (int u = 0; u < %d; ++u) {" % R)
+    for j, ((col, rep), (arr, idx)) in enumerate(cols):
+        if rep == "f64":
+            L.append("                dep ^= (unsigned)__double2loint(%s[u]) ^ (unsigned)__double2hiint(%s[u]);" % (arr, arr))
+        else:
+            L.append("                dep ^= (unsigned)%s[u];" % arr)
+    L.append("            }")
+    L.append("            dep = __reduce_or_sync(0xffffffffu, dep);  // all lanes' loads have returned")
+    L.append("            // (S >> 8) is 0 at run time (S <= 8) but not to the compiler: the address really depends on dep")
+    L.append("            if ((threadIdx.x & 31) == 0) sdqlrt::mbar_arrive(empty + rs + (dep & (unsigned)(S >> 8)));")
     L.append("            if (threadIdx.x == 0) {")
     L.append("                const long long kn = k + (long long)S * gridDim.x;")
     L.append("                if (kn < nfull) { sdqlrt::mbar_wait(empty + rs, rph); issue(rs, kn); }")
@@ -1596,7 +1610,14 @@ def merge_code(q, K):
         cop = " || ".join("((a->cols[%d].flags & SDQLB200_COL_PARTKEY) != 0)" % p[1] for p in t.parts if p[0] == "col") or "false"
         L.append("        part_%s = true;  // iteration over this table is partitioned (by key range or by owner rank)" % t.name)
         L.append("        if (!(%s)) {" % cop)
-        L.append("            if (!c.%s.direct) return sdqlhost::fail(SDQLB200_E_ARG, \"%s: table %s is hashed; cross-GPU shuffle of hashed partial tables is not implemented\");" % (t.name, q.name, t.name))
+        L.append("            if (!c.%s.direct) {  // hashed partial dictionary: hash all-to-all + combine + all-gather (SDQLB200_MERGE_TABLE)" % t.name)
+        L.append("                sdqlb200_table td; memset(&td, 0, sizeof td);")
+        L.append("                td.keys = (uint64_t*)c.%s.keys; td.rep = c.%s.rep; td.cap = c.%s.cap; td.nfields = %d; td.f64_mask = %du;" %
+                 (t.name, t.name, t.name, len(t.fields), sum(1 << j for j, (_, ct) in enumerate(t.fields) if ct == "f64")))
+        for j in range(len(t.fields)):
+            L.append("                td.agg[%d] = c.%s_a%d;" % (j, t.name, j))
+        L.append("                if (a->merge(a->merge_ctx, (unsigned long long)(uintptr_t)&td, 0, SDQLB200_MERGE_TABLE)) return sdqlhost::fail(SDQLB200_E_ARG, \"%s: merging hashed table %s across ranks failed\");" % (q.name, t.name))
+        L.append("            } else {")
         L.append("            const int og = sdqlhost::grid_for(c.%s.cap, 8, sms);" % t.name)
         L.append("            SDQL_LAUNCH(sdqlrt::k_owner_encode, og, sdqlrt::kBlock, 0, st, c.%s.rep, own_%s, c.%s.cap, a->rank);" % (t.name, t.name, t.name))
         L.append("            if (a->merge(a->merge_ctx, %s, (unsigned long long)c.%s.cap, SDQLB200_MIN_I32)) return sdqlhost::fail(SDQLB200_E_ARG, \"merge callback failed\");" % (off % ("own_%s" % t.name), t.name))
@@ -1611,6 +1632,7 @@ def merge_code(q, K):
             L.append("            if (a->merge(a->merge_ctx, %s, %s, %s)) return sdqlhost::fail(SDQLB200_E_ARG, \"merge callback failed\");" %
                      (off % ("c.%s_a%d" % (t.name, j)), cnt, "SDQLB200_SUM_F64" if ct == "f64" else "SDQLB200_SUM_I64"))
             j = k + 1
+        L.append("            }")
         L.append("        }")
     L.append("    }")
     return L
@@ -1891,6 +1913,45 @@ void sdqlb200_result_free(sdqlb200_result* r) {
     if (!r) return;
     for (int j = 0; j < 32; ++j) { free(r->cols[j]); r->cols[j] = nullptr; }
     r->count = 0;
+}
+
+static int sdql_tbl_io(const sdqlb200_table* t, sdqlrt::TblIO* io) {
+    if (!t || !t->keys || t->nfields < 0 || t->nfields > 16 || t->cap < 1 || (t->cap & (t->cap - 1)))
+        return sdqlhost::fail(SDQLB200_E_ARG, "bad table descriptor");
+    io->keys = (sdqlrt::u64*)t->keys; io->rep = t->rep; io->cap = t->cap; io->nf = t->nfields; io->f64_mask = t->f64_mask;
+    for (int j = 0; j < 16; ++j) io->agg[j] = (sdqlrt::u64*)t->agg[j];
+    return SDQLB200_OK;
+}
+int sdqlb200_table_count(const sdqlb200_table* t, int32_t world, uint64_t* d_counts, void* stream) {
+    sdqlrt::TblIO io;
+    if (int rc = sdql_tbl_io(t, &io)) return rc;
+    if (world < 1 || !d_counts) return sdqlhost::fail(SDQLB200_E_ARG, "table_count: bad arguments");
+    SDQL_LAUNCH(sdqlrt::k_tbl_count, sdqlhost::grid_for(io.cap, 8, sdqlhost_sms()), sdqlrt::kBlock, 0, stream, io, world,
+                (sdqlrt::u64*)d_counts);
+    SDQL_CUDA(cudaGetLastError());
+    return SDQLB200_OK;
+}
+int sdqlb200_table_pack(const sdqlb200_table* t, int32_t world, int32_t rank, const int32_t* d_own,
+                        const uint64_t* d_offsets, uint64_t* d_cursor, int64_t* d_records, void* stream) {
+    sdqlrt::TblIO io;
+    if (int rc = sdql_tbl_io(t, &io)) return rc;
+    if (world < 1 || !d_offsets || !d_cursor || !d_records) return sdqlhost::fail(SDQLB200_E_ARG, "table_pack: bad arguments");
+    SDQL_LAUNCH(sdqlrt::k_tbl_pack, sdqlhost::grid_for(io.cap, 8, sdqlhost_sms()), sdqlrt::kBlock, 0, stream, io, world, rank,
+                (const int*)d_own, (const sdqlrt::u64*)d_offsets, (sdqlrt::u64*)d_cursor, (sdqlrt::i64*)d_records);
+    SDQL_CUDA(cudaGetLastError());
+    return SDQLB200_OK;
+}
+int sdqlb200_table_absorb(const sdqlb200_table* t, const int64_t* d_records, int64_t n, int32_t mode, int32_t rank,
+                          int32_t* d_own, void* stream) {
+    sdqlrt::TblIO io;
+    if (int rc = sdql_tbl_io(t, &io)) return rc;
+    if (n < 0 || (n > 0 && !d_records) || (mode == 0 && !d_own) || (mode == 1 && !io.rep))
+        return sdqlhost::fail(SDQLB200_E_ARG, "table_absorb: bad arguments");
+    if (n == 0) return SDQLB200_OK;
+    SDQL_LAUNCH(sdqlrt::k_tbl_absorb, sdqlhost::grid_for(n, 8, sdqlhost_sms()), sdqlrt::kBlock, 0, stream, io,
+                (const sdqlrt::i64*)d_records, (sdqlrt::i64)n, mode, rank, (int*)d_own);
+    SDQL_CUDA(cudaGetLastError());
+    return SDQLB200_OK;
 }
 }
 '''

@@ -72,8 +72,10 @@ static inline bool size_table(sdqlrt::Tbl* t, int nparts, const long long* mn, c
     }
     if (src_rows < 1) src_rows = 1;
     long long domain = (long long)dom;
-    // direct when the dense array is not (much) bigger than what a hash table for src_rows keys would need
-    bool direct = dom <= (long double)(8 * src_rows + 65536) && domain < (1ll << 31);
+    // direct when the dense array is not (much) bigger than what a hash table for src_rows keys would need.
+    // SDQLB200_FORCE_HASH=1 (debug knob): never direct -- exercises the hash build / probe / merge paths at small scale
+    static const bool force_hash = getenv("SDQLB200_FORCE_HASH") && getenv("SDQLB200_FORCE_HASH")[0] == '1';
+    bool direct = !force_hash && dom <= (long double)(8 * src_rows + 65536) && domain < (1ll << 31);
     t->direct = direct ? 1 : 0;
     if (direct) {
         t->cap = domain;

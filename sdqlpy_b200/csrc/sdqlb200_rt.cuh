@@ -267,6 +267,75 @@ __global__ void k_owner_decode(int* rep, const int* own, long long cap, int rank
 }
 
 // ---------------------------------------------------------------------------------------------
+// cross-GPU merge of a HASHED table ("all-reduce of a dictionary" = hash all-to-all + all-gather):
+//   count/pack   every occupied slot becomes one record [key, owner rank, field 0 .. field nf-1] (8-byte words),
+//                grouped by destination rank = hash(key) mod world                         -> NCCL all-to-all
+//   absorb(0)    the destination combines the records of all ranks in a scratch table (sum of the fields, owner = the
+//                lowest rank that saw the key); its entries are packed again                -> NCCL all-gather
+//   absorb(1)    every rank writes the combined entries back into its own table: fields := global sums, slots owned by
+//                another rank get rep = -2 (present for probes, skipped when the table is iterated)
+// ---------------------------------------------------------------------------------------------
+struct TblIO {
+    u64* keys;
+    int* rep;
+    i64 cap;
+    int nf;
+    unsigned f64_mask;  // bit j: field j is fp64 (else int64)
+    u64* agg[16];
+};
+SDQL_DEV int shuffle_dest(u64 key, int world) { return (int)((hash64(key ^ 0x9e3779b97f4a7c15ull) >> 33) % (u64)world); }
+
+__global__ void k_tbl_count(TblIO t, int world, u64* counts) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < t.cap; i += (i64)gridDim.x * blockDim.x) {
+        const u64 k = t.keys[i];
+        if (k != kEmpty) atomicAdd(counts + shuffle_dest(k, world), 1ull);
+    }
+}
+// own == nullptr: owner word = rank (first hop); else owner word = own[slot] (second hop, scratch table)
+__global__ void k_tbl_pack(TblIO t, int world, int rank, const int* own, const u64* offsets, u64* cursor, i64* rec) {
+    const int W = 2 + t.nf;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < t.cap; i += (i64)gridDim.x * blockDim.x) {
+        const u64 k = t.keys[i];
+        if (k == kEmpty) continue;
+        const int d = shuffle_dest(k, world);
+        const u64 pos = offsets[d] + atomicAdd(cursor + d, 1ull);
+        i64* r = rec + pos * W;
+        r[0] = (i64)k;
+        r[1] = own ? (i64)own[i] : (i64)rank;
+        for (int j = 0; j < t.nf; ++j) r[2 + j] = (i64)t.agg[j][i];
+    }
+}
+__global__ void k_tbl_absorb(TblIO t, const i64* rec, i64 n, int mode, int rank, int* own) {
+    const int W = 2 + t.nf;
+    const u64 m = (u64)t.cap - 1;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const i64* r = rec + i * W;
+        const u64 key = (u64)r[0];
+        u64 h = hash64(key) & m;
+        bool claimed = false;
+        for (;;) {  // find or claim (the table is sized for the union of all ranks' keys)
+            u64 k = t.keys[h];
+            if (k == kEmpty) {
+                k = atomicCAS(t.keys + h, kEmpty, key);
+                if (k == kEmpty) { claimed = true; break; }
+            }
+            if (k == key) break;
+            h = (h + 1) & m;
+        }
+        if (mode == 0) {
+            for (int j = 0; j < t.nf; ++j) {
+                if ((t.f64_mask >> j) & 1u) red_add((double*)t.agg[j] + h, __longlong_as_double(r[2 + j]));
+                else red_add((i64*)t.agg[j] + h, r[2 + j]);
+            }
+            atomicMin(own + h, (int)r[1]);
+        } else {
+            for (int j = 0; j < t.nf; ++j) t.agg[j][h] = (u64)r[2 + j];
+            if ((int)r[1] != rank || claimed) t.rep[h] = -2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // fixed-width, zero-padded byte strings (device form of VarChar<N>, 1 byte per char)
 // ---------------------------------------------------------------------------------------------
 SDQL_DEV int str_len(const unsigned char* s, int w) {

@@ -43,7 +43,12 @@ class Args(ctypes.Structure):
                 ("tier", ctypes.c_int32), ("reserved", ctypes.c_int32), ("result", Result),
                 ("kernel_ms", ctypes.c_float * 24), ("merge", ctypes.c_void_p), ("merge_ctx", ctypes.c_void_p),
                 ("part_mask", ctypes.c_uint32), ("result_partial", ctypes.c_int32), ("rank", ctypes.c_int32),
-                ("reserved2", ctypes.c_int32)]
+                ("world", ctypes.c_int32)]
+
+
+class Table(ctypes.Structure):  # == sdqlb200_table
+    _fields_ = [("keys", ctypes.c_void_p), ("rep", ctypes.c_void_p), ("cap", ctypes.c_int64),
+                ("nfields", ctypes.c_int32), ("f64_mask", ctypes.c_uint32), ("agg", ctypes.c_void_p * 16)]
 
 
 MERGE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int32)
@@ -344,6 +349,10 @@ class CompiledModule:
         self.lib.sdqlb200_last_error.restype = ctypes.c_char_p
         self.lib.sdqlb200_run.argtypes = [ctypes.c_char_p, ctypes.POINTER(Args)]
         self.lib.sdqlb200_result_free.argtypes = [ctypes.POINTER(Result)]
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+        self.lib.sdqlb200_table_count.argtypes = [ctypes.POINTER(Table), i32, vp, vp]
+        self.lib.sdqlb200_table_pack.argtypes = [ctypes.POINTER(Table), i32, i32, vp, vp, vp, vp, vp]
+        self.lib.sdqlb200_table_absorb.argtypes = [ctypes.POINTER(Table), vp, i64, i32, i32, vp, vp]
         man = json.loads(self.lib.sdqlb200_manifest().decode())
         self.queries = {q["name"]: q for q in man["queries"]}
         self.ws = None
@@ -413,7 +422,7 @@ class CompiledModule:
             if self._merge_cb is None:
                 self._merge_cb = MERGE_FN(self._merge)
             a.merge = ctypes.cast(self._merge_cb, ctypes.c_void_p)
-            a.rank = DIST.rank
+            a.rank, a.world = DIST.rank, DIST.world
         rc = self.lib.sdqlb200_run(name.encode(), ctypes.byref(a))
         if rc == E_WORKSPACE:
             need = int(a.workspace_needed)
@@ -434,7 +443,9 @@ class CompiledModule:
             d = DIST.dist
             ws = self.ws[1]
             t = ws if isinstance(ws, torch.Tensor) else torch.from_numpy(ws)
-            if op == 0:
+            if op == 3:
+                self._merge_table(Table.from_address(off))
+            elif op == 0:
                 d.all_reduce(t[off:off + 8 * count].view(torch.float64), op=d.ReduceOp.SUM, group=DIST.group)
             elif op == 1:
                 d.all_reduce(t[off:off + 8 * count].view(torch.int64), op=d.ReduceOp.SUM, group=DIST.group)
@@ -445,6 +456,70 @@ class CompiledModule:
         except Exception as e:  # never let an exception cross the C boundary
             self.merge_error = e
             return 1
+
+    def _merge_table(self, t):
+        """SDQLB200_MERGE_TABLE: all-reduce of a hashed partial dictionary (SURVEY.md 8e "hash all-to-all shuffle").
+        1. every rank packs its entries grouped by destination rank = hash(key) mod world   (sdqlb200_table_count/pack)
+        2. all-to-all of the runs (NCCL over NVLink; gloo in the CPU tests)
+        3. the destination combines what it received in a scratch table: fields summed, owner = lowest source rank
+        4. all-gather of the combined entries; every rank writes them back into its own table (fields := global sums,
+           entries owned by another rank get rep = -2: visible to probes, skipped when the table is iterated)"""
+        import torch
+        d, world, rank = DIST.dist, DIST.world, DIST.rank
+        dev = self.ws[1].device if isinstance(self.ws[1], torch.Tensor) else torch.device("cpu")
+        st = backend().stream()
+        L, W = self.lib, 2 + int(t.nfields)
+
+        def ck(rc, what):
+            if rc != 0:
+                raise RuntimeError("%s failed (%d): %s" % (what, rc, L.sdqlb200_last_error().decode()))
+
+        def pack(tab, nranks, own):
+            cnt = torch.zeros(nranks, dtype=torch.int64, device=dev)
+            ck(L.sdqlb200_table_count(ctypes.byref(tab), nranks, cnt.data_ptr(), st), "table_count")
+            host = cnt.cpu()
+            offs = (torch.cumsum(host, 0) - host).to(dev)
+            cur = torch.zeros(nranks, dtype=torch.int64, device=dev)
+            rec = torch.empty((max(int(host.sum()), 1), W), dtype=torch.int64, device=dev)
+            ck(L.sdqlb200_table_pack(ctypes.byref(tab), nranks, rank, own, offs.data_ptr(), cur.data_ptr(),
+                                     rec.data_ptr(), st), "table_pack")
+            return rec, host
+
+        send, cnt = pack(t, world, None)
+        rcnt = torch.empty(world, dtype=torch.int64, device=dev)
+        d.all_to_all_single(rcnt, cnt.to(dev), group=DIST.group)
+        rcnt = rcnt.cpu()
+        nrecv = int(rcnt.sum())
+        recv = torch.empty((max(nrecv, 1), W), dtype=torch.int64, device=dev)
+        d.all_to_all_single(recv[:nrecv], send[:int(cnt.sum())], rcnt.tolist(), cnt.tolist(), group=DIST.group)
+        # combine at the destination
+        cap2 = 1024
+        while cap2 < 2 * nrecv:
+            cap2 <<= 1
+        keys2 = torch.full((cap2,), -1, dtype=torch.int64, device=dev)
+        own2 = torch.full((cap2,), 0x7fffffff, dtype=torch.int32, device=dev)
+        agg2 = torch.zeros((max(int(t.nfields), 1), cap2), dtype=torch.int64, device=dev)
+        t2 = Table()
+        t2.keys, t2.rep, t2.cap, t2.nfields, t2.f64_mask = keys2.data_ptr(), own2.data_ptr(), cap2, t.nfields, t.f64_mask
+        for j in range(int(t.nfields)):
+            t2.agg[j] = agg2[j].data_ptr()
+        ck(L.sdqlb200_table_absorb(ctypes.byref(t2), recv.data_ptr(), nrecv, 0, rank, own2.data_ptr(), st), "table_absorb")
+        mine, m = pack(t2, 1, own2.data_ptr())
+        m = int(m[0])
+        # all-gather of the combined runs (padded to the longest)
+        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        d.all_gather(sizes, torch.tensor([m], dtype=torch.int64, device=dev), group=DIST.group)
+        sizes = [int(x) for x in sizes]
+        if 2 * sum(sizes) > int(t.cap):
+            raise RuntimeError("merged dictionary has %d entries, the table was sized for %d slots" % (sum(sizes), int(t.cap)))
+        mx = max(max(sizes), 1)
+        padded = torch.zeros((mx, W), dtype=torch.int64, device=dev)
+        padded[:m] = mine[:m]
+        parts = [torch.empty((mx, W), dtype=torch.int64, device=dev) for _ in range(world)]
+        d.all_gather(parts, padded, group=DIST.group)
+        for r in range(world):
+            ck(L.sdqlb200_table_absorb(ctypes.byref(t), parts[r].data_ptr(), sizes[r], 1, rank, None, st), "table_absorb")
+        self.table_merges = getattr(self, "table_merges", 0) + 1
 
     def run(self, name, db):
         h2d0 = STORE.h2d_bytes

@@ -45,7 +45,7 @@ def _worker(rank, world, so, port, queries, out):
         if d is not None:
             bad.append((q, d))
     if rank == 0:
-        open(out, "w").write(repr(bad) + "\n%d" % mod.merges)
+        open(out, "w").write(repr(bad) + "\n%d\n%d" % (mod.merges, getattr(mod, "table_merges", 0)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,6 +64,27 @@ def emu_so(tmp_path_factory):
 def test_world2_partitioned_queries_match_reference(emu_so, tmp_path):
     out = str(tmp_path / "res.txt")
     mp.spawn(_worker, args=(2, emu_so, 29731, SUPPORTED, out), nprocs=2, join=True)
-    bad, merges = open(out).read().split("\n")
+    bad, merges, tmerges = open(out).read().split("\n")
     assert bad == "[]", bad
-    assert int(merges) > 0
+    assert int(merges) > 0 and int(tmerges) == 0
+
+
+def test_world2_hashed_partial_dictionaries_are_shuffled(emu_so, tmp_path, monkeypatch):
+    """every table hashed (SDQLB200_FORCE_HASH): partial dictionaries built from partitioned relations go through the
+    hash all-to-all + combine + all-gather merge (SDQLB200_MERGE_TABLE) instead of the dense all-reduce."""
+    monkeypatch.setenv("SDQLB200_FORCE_HASH", "1")
+    out = str(tmp_path / "res.txt")
+    mp.spawn(_worker, args=(2, emu_so, 29733, SUPPORTED, out), nprocs=2, join=True)
+    bad, merges, tmerges = open(out).read().split("\n")
+    assert bad == "[]", bad
+    assert int(tmerges) > 0
+
+
+def test_world3_hashed_shuffle(emu_so, tmp_path, monkeypatch):
+    """three ranks: uneven runs in the all-to-all, owners that never saw the key locally."""
+    monkeypatch.setenv("SDQLB200_FORCE_HASH", "1")
+    out = str(tmp_path / "res.txt")
+    mp.spawn(_worker, args=(3, emu_so, 29735, ["q1", "q13", "q15", "q17", "q20", "q22", "q10"], out), nprocs=3, join=True)
+    bad, merges, tmerges = open(out).read().split("\n")
+    assert bad == "[]", bad
+    assert int(tmerges) > 0

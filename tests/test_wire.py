@@ -145,7 +145,9 @@ def test_device_decode_bit_exact(rows):
         wire.FIXED32_F64: rng.integers(-99999, 10_500_000, rows) / 100.0,
     }
     for kind, a in cols.items():
-        if rows < 1024:  # below the packing threshold: build the packed image by hand
+        if rows < 1024 or (kind == wire.FIXED32_F64 and rows <= 65536):
+            # below the packing threshold (or few enough distinct values that the encoder would prefer a dictionary):
+            # build the packed image by hand
             if kind == wire.FIXED32_F64:
                 p = wire.Packed(kind, np.rint(a * 100).astype(np.int32), None, 100.0, "f64")
             else:
