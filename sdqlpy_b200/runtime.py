@@ -545,9 +545,9 @@ class CompiledModule:
             cols = [np.concatenate([p[j] for p in parts]) for j in range(nf)]
             n = len(cols[0]) if cols else 0
             info.rows = n
-        return self.box(q, db, cols, n)
+        return self.box(q, db, cols, n, keep[0])
 
-    def box(self, q, db, cols, n):
+    def box(self, q, db, cols, n, dev_cols=None):
         kind = q["result_kind"]
         if kind == "f64":
             return float(cols[0].view(np.float64)[0])
@@ -572,7 +572,11 @@ class CompiledModule:
                 _, _, arg, col = fk.split(":")
                 cn = [x for x, _ in q["schemas"][arg]]
                 kindc = dict((x, k) for x, k in q["schemas"][arg])[col]
-                d = STORE.get(db[argpos[arg]][cn.index(col)], "code", kindc[1]).dictionary
+                key = [arg, col, "code"]
+                if dev_cols is not None and key in q["inputs"]:
+                    d = dev_cols[q["inputs"].index(key)].dictionary  # the dictionary of the column the kernels read
+                else:
+                    d = STORE.get(db[argpos[arg]][cn.index(col)], "code", kindc[1]).dictionary
                 decoders.append(lambda c, d=d: [d[i] for i in c])
             elif fk.startswith("str:pack:"):
                 nb = int(fk.split(":")[2])
