@@ -187,13 +187,14 @@ def main():
         wire.pack_column(col)
         if col.wire is not None:
             col.wire.pin(be)
-            wire_cols.append("%s:%s:%d" % (c, wire.KIND_NAMES[col.wire.kind], col.wire.codes.itemsize))
-            wire_bpr += col.wire.codes.itemsize
+            bits = col.wire.nbits if col.wire.nbits else 8 * col.wire.codes.itemsize
+            wire_cols.append("%s:%s:%db" % (c, wire.KIND_NAMES[col.wire.kind], bits))
+            wire_bpr += bits / 8.0
         else:
             v, t = be.pinned_like(col.data)
             col.data = v
             keep.append(t)
-            wire_cols.append("%s:plain:%d" % (c, col.data.itemsize))
+            wire_cols.append("%s:plain:%db" % (c, 8 * col.data.itemsize))
             wire_bpr += col.data.itemsize
     t_pack = time.perf_counter() - t_pack
     db = [[cols.get(c) for c in names]]

@@ -45,6 +45,9 @@ PIPELINE = os.environ.get("SDQLB200_PIPELINE", "auto")  # auto | tma | reg | l2 
 PF_DIST = int(os.environ.get("SDQLB200_PF_DIST", "2"))
 RING_ROWS_PER_THREAD = int(os.environ.get("SDQLB200_RING_ROWS", "0"))  # 0 = per kernel (Kernel.ring_rows)
 RING_MAX_ROW_BYTES = 100     # wider scans cannot keep two stages in 227 KB of shared memory: they use LDGs
+BYTE_STAGING = os.environ.get("SDQLB200_BYTE_STAGING", "1") != "0"  # string columns of the scanned row go through shared memory
+BITS_FILTER = os.environ.get("SDQLB200_BITS", "1") != "0"  # presence bitmaps in front of selective, probed tables
+COUNT_PASS = os.environ.get("SDQLB200_COUNT_PASS", "1") != "0"  # cardinality passes in front of selective table builds
 
 
 # =============================================================================================
@@ -161,6 +164,7 @@ class TableDesc:
         self.key_fn = None      # (K, idx_code) -> key SValue   (rep-evaluation)
         self.val_fn = None      # build: (K, idx_code) -> value SValue
         self.inner = None       # nested dict value: (n_outer_parts, [inner stats], inner key template SValue)
+        self.probed = False     # looked up by some kernel (tbl_find): candidates for a presence filter
         self.distinct_of = None
 
     # -- element access ---------------------------------------------------------------------
@@ -303,6 +307,35 @@ class Kernel:
         self.smem_expr = "0"
         self.tier_expr = "2"
         self.scan_var = "i"
+        self.byte_cols = OrderedDict()  # input idx -> width: fixed-width string columns staged through shared memory
+        self.counted = False      # has a cardinality-pass variant (TIER == 3): predicates in front of a table build
+        self.pred_cols = None     # scan columns the predicates read (the only ones the cardinality pass loads)
+
+    @property
+    def templated(self):
+        return self.tiered or self.counted
+
+    def enable_count(self):
+        """cardinality pass (TIER == 3): the same scan + predicates + probes, but every row that reaches the sink is only
+        counted.  The host sizes the kernel's tables from that count instead of the source's row count, so selective
+        builds get small (cache-resident) tables and cheap initialisation."""
+        if self.counted:
+            return
+        self.counted = True
+        self.count_slot = self.q.ntcount
+        self.q.ntcount += 1
+        self.pre.append("unsigned long long cnt_rows = 0;")
+        self.post.append("if (TIER == 3) {")
+        self.post.append("    const long long s_ = sdqlrt::block_sum((long long)cnt_rows);")
+        self.post.append("    if (threadIdx.x == 0 && s_) atomicAdd(c.tcount + %d, (unsigned long long)s_);" % self.count_slot)
+        self.post.append("    return;")
+        self.post.append("}")
+
+    def count_guard(self, col, rep):
+        """loads of columns that only the sink reads are skipped by the cardinality pass"""
+        if self.counted and self.pred_cols is not None and (col, rep) not in self.pred_cols:
+            return "if (TIER != 3) "
+        return ""
 
     def emit(self, s):
         self.body.append("    " * self.depth + s)
@@ -367,10 +400,10 @@ class Kernel:
     def render(self):
         q = self.q
         L = []
-        tmpl = "template <int TIER>\n" if self.tiered else ""
+        tmpl = "template <int TIER>\n" if self.templated else ""
         L.append("%s__global__ void __launch_bounds__(sdqlrt::kBlock) %s(const __grid_constant__ %s_ctx c) {" %
                  (tmpl, self.name, q.name))
-        if self.tiered or self.pipe_mode() == "tma":
+        if self.tiered or self.pipe_mode() == "tma" or self.byte_cols:
             L.append("    SDQL_EXTERN_SMEM(sm);")
         L += ["    " + s for s in self.pre]
         if self.src[0] == "rel" and self.pipe_mode() == "tma":
@@ -387,19 +420,21 @@ class Kernel:
                 o.append(ind + "    if (j0 + 4 <= n) {")
                 for (col, rep), (arr, idx) in self.scan_cols.items():
                     dst = prefix + arr[2:]
+                    cg = self.count_guard(col, rep)
                     if rep == "code":
-                        o.append(ind + "        sdqlrt::ld4_code(c.in%d, j0, c.in%d_w, %s);" % (idx, idx, dst))
+                        o.append(ind + "        %ssdqlrt::ld4_code(c.in%d, j0, c.in%d_w, %s);" % (cg, idx, idx, dst))
                     else:
-                        o.append(ind + "        sdqlrt::ld4(c.in%d + j0, %s);" % (idx, dst))
+                        o.append(ind + "        %ssdqlrt::ld4(c.in%d + j0, %s);" % (cg, idx, dst))
                 o.append(ind + "    } else {")
                 o.append(ind + "        for (int u = 0; u < 4; ++u) {")
                 o.append(ind + "            const long long ii = (j0 + u < n) ? j0 + u : n - 1;")
                 for (col, rep), (arr, idx) in self.scan_cols.items():
                     dst = prefix + arr[2:]
+                    cg = self.count_guard(col, rep)
                     if rep == "code":
-                        o.append(ind + "            %s[u] = sdqlrt::ld1_code(c.in%d, ii, c.in%d_w);" % (dst, idx, idx))
+                        o.append(ind + "            %s%s[u] = sdqlrt::ld1_code(c.in%d, ii, c.in%d_w);" % (cg, dst, idx, idx))
                     else:
-                        o.append(ind + "            %s[u] = sdqlrt::ld1(c.in%d + ii);" % (dst, idx))
+                        o.append(ind + "            %s%s[u] = sdqlrt::ld1(c.in%d + ii);" % (cg, dst, idx))
                 o.append(ind + "        }")
                 o.append(ind + "    }")
                 o.append(ind + "}")
@@ -409,27 +444,41 @@ class Kernel:
             L.append("    const long long ngrp = (n + 3) >> 2;")
             L.append("    const long long gstride = (long long)gridDim.x * blockDim.x;")
             L.append("    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
+            loop_cond = "g < ngrp"
+            if self.byte_cols:
+                # every lane of a warp runs the same number of iterations (the warp stages its rows cooperatively)
+                loop_cond = "g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp"
+                boff = 0
+                for idx, w in self.byte_cols.items():
+                    L.append("    unsigned char* const bs%d = (unsigned char*)sm + c.%s_bo + %du + (threadIdx.x / sdqlrt::kLanes) * %du;" %
+                             (idx, self.name, boff, 128 * w))
+                    boff += 1024 * w
+            stage = ["        sdqlrt::stage_rows(bs%d, c.in%d, (g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1))) << 2, n, %d);" % (idx, idx, w)
+                     for idx, w in self.byte_cols.items()]
             pipe = self.pipe_mode() or "reg"
             if pipe == "reg":
                 for (col, rep), (arr, idx) in self.scan_cols.items():
                     L.append("    %s %s[4], %s[4];" % (ety[rep], arr, "q_" + arr[2:]))
                 L.append("    if (g < ngrp)")
                 L += loads("r_", "g", "    ")
-                L.append("    while (g < ngrp) {")
+                L.append("    while (%s) {" % loop_cond)
                 L.append("        const long long gn = g + gstride;")
                 L.append("        if (gn < ngrp)")
                 L += loads("q_", "gn", "        ")
+                L += stage
             else:  # "l2": single register buffer, the group PF_DIST iterations ahead is prefetched into L2
                 for (col, rep), (arr, idx) in self.scan_cols.items():
                     L.append("    %s %s[4];" % (ety[rep], arr))
-                L.append("    while (g < ngrp) {")
+                L.append("    while (%s) {" % loop_cond)
                 L.append("        const long long gn = g + gstride;")
+                L += stage
                 L.append("        { const long long gp = g + %d * gstride; if (gp < ngrp) {" % PF_DIST)
                 for (col, rep), (arr, idx) in self.scan_cols.items():
+                    cg = self.count_guard(col, rep)
                     if rep == "code":
-                        L.append("            sdqlrt::prefetch_l2((const char*)c.in%d + (gp << 2) * c.in%d_w);" % (idx, idx))
+                        L.append("            %ssdqlrt::prefetch_l2((const char*)c.in%d + (gp << 2) * c.in%d_w);" % (cg, idx, idx))
                     else:
-                        L.append("            sdqlrt::prefetch_l2(c.in%d + (gp << 2));" % idx)
+                        L.append("            %ssdqlrt::prefetch_l2(c.in%d + (gp << 2));" % (cg, idx))
                 L.append("        } }")
                 L += loads("r_", "g", "        ")
             L.append("        const long long i0 = g << 2;")
@@ -673,6 +722,17 @@ def is_true(v):
 class KeyedSink:
     """shared by BuildSink / GroupSink: FD-minimised, mixed-radix packed keys."""
 
+    def count_open(self):
+        K = self.K
+        if K.sink is self and K.counted:  # cardinality pass: the row is counted instead of inserted
+            K.emit("if (TIER == 3) { ++cnt_rows; }")
+            K.open_block("else")
+
+    def count_close(self):
+        K = self.K
+        if K.sink is self and K.counted:
+            K.close()
+
     def setup_key(self, t, keyval, extra_parts=()):
         q, K = self.q, self.K
         leaves = flatten(K, keyval)
@@ -716,8 +776,10 @@ class BuildSink(KeyedSink):
 
     def produce(self, d):
         K, t = self.K, self.t
+        self.count_open()
         kk = self.pack(t, self.setup_key(t, d.k))
         K.emit("if (%s_ok) { bool nw; sdqlrt::tbl_upsert(c.%s, %s, (int)%s, nw); }" % (kk, t.name, kk, K.scan_var))
+        self.count_close()
 
     def finish(self):
         return STable(self.t)
@@ -733,6 +795,11 @@ class GroupSink(KeyedSink):
         self.tc = None
 
     def produce(self, d):
+        self.count_open()
+        self.produce_(d)
+        self.count_close()
+
+    def produce_(self, d):
         q, K, t = self.q, self.K, self.t
         v = unwrap(d.v)
         extra, inner_leaves = [], None
@@ -848,7 +915,7 @@ class GroupSink(KeyedSink):
                     else:
                         P.append("        const long long v%d = sdqlrt::block_sum((long long)ra%d_%d);" % (j, j, sl_))
                 P.append("        if (threadIdx.x == 0 && r >= 0) {")
-                P.append("            atomicMax(c.%s.rep + %d, r);" % (t.name, sl_))
+                P.append("            atomicMax(c.%s.rep + %d, r); sdqlrt::tbl_mark(c.%s, %dull);" % (t.name, sl_, t.name, sl_))
                 for j, (_, ct) in enumerate(t.fields):
                     P.append("            sdqlrt::red_add(c.%s_a%d + %d, v%d);" % (t.name, j, sl_, j))
                 P.append("        }")
@@ -858,7 +925,7 @@ class GroupSink(KeyedSink):
             P.append("    for (long long k = threadIdx.x; k < ncap; k += blockDim.x) {")
             P.append("        int r = smrep[k];")
             P.append("        if (r >= 0) {")
-            P.append("            atomicMax(c.%s.rep + k, r);" % t.name)
+            P.append("            atomicMax(c.%s.rep + k, r); sdqlrt::tbl_mark(c.%s, (unsigned long long)k);" % (t.name, t.name))
             for j, (_, ct) in enumerate(t.fields):
                 if ct == "f64":
                     P.append("            sdqlrt::red_add(c.%s_a%d + k, __longlong_as_double(sm[k * %d + %d]));" % (t.name, j, nf, j))
@@ -953,6 +1020,7 @@ class Query:
         self.nsc = 0
         self.npart = []
         self.ncnt = 0
+        self.ntcount = 0
         self.token_deps = {}
         self.ntok = 0
         self.result_schema = None
@@ -1042,6 +1110,10 @@ class Query:
         if s.kind != "ref":
             raise CodegenError("pattern functions need a column string")
         idx = self.input(s.arg, s.col, "bytes")
+        if s.scan and K is not None and K.src == ("rel", s.arg) and PIPELINE != "tma" and BYTE_STAGING:
+            # the scanned row's bytes come from the warp's shared-memory staging buffer (Kernel.render / stage_rows)
+            K.byte_cols[idx] = s.width
+            return "(bs%d + (unsigned)(((threadIdx.x & (sdqlrt::kLanes - 1)) << 2) + u) * %du)" % (idx, s.width), s.width
         return "(c.in%d + (long long)(%s) * %d)" % (idx, s.row if not s.scan else "i", s.width), s.width
 
     def part_code(self, K, x):
@@ -1224,11 +1296,15 @@ class Query:
             return self.nested_sum(e, env, K)
         if isinstance(e, (ir.EmptyDicConsExpr,)) or (isinstance(e, ir.ConstantExpr) and e.value is None):
             return
+        if K.sink is None and K.pred_cols is None:
+            K.pred_cols = set(K.scan_cols)  # everything read so far was read by predicates / probes
         v = self.ev(e, env, K)
         if K.sink is None:
             K.sink = self.make_sink(K, v)
             if isinstance(K.sink, (BuildSink, GroupSink)):
                 self.bind_table_fns(K, K.sink.t, e, env)
+                if K.depth > 0 and K.src[0] in ("rel", "tbl") and COUNT_PASS:
+                    K.enable_count()
         K.sink.produce(v)
         if isinstance(K.sink, ReduceSink) and isinstance(e, ir.RecConsExpr):
             for name, fe in e.initialPairs:
@@ -1273,6 +1349,8 @@ class Query:
             raise CodegenError("nested dictionaries need a single dictionary-coded inner key")
         idx = inner_stats[0][1]
         cv = K.tmp("cv")
+        # a presence filter on the outer key part rejects the whole inner dictionary at once
+        K.open_if("%s_outer_ok && (c.%s.bmod == 0 || sdqlrt::tbl_maybe(c.%s, %s_outer))" % (d.slot, t.name, t.name, d.slot))
         K.open_block("for (long long %s = c.%s_mn[%d]; %s < c.%s_mn[%d] + c.%s_rng[%d]; ++%s)" %
                      (cv, t.name, n_outer, cv, t.name, n_outer, t.name, n_outer, cv))
         kk = K.tmp("kk")
@@ -1292,11 +1370,13 @@ class Query:
         self.run_body(S.bodyExpr, env2, K)
         K.close()
         K.close()
+        K.close()
 
     # -- lookups ----------------------------------------------------------------------------------
     def lookup(self, K, t, keyval):
         if K is None:
             raise CodegenError("dictionary lookup outside of a sum body")
+        t.probed = True
         leaves = flatten(K, keyval)
         n_expected = len(t.parts) if t.inner is None else t.inner[0]
         # the probe key has the build key's *full* shape; keep the positions the build kept by value
@@ -1661,9 +1741,11 @@ def render_query(q):
         for j, (_, ct) in enumerate(t.fields):
             L.append("    %s* %s_a%d;" % (CT[ct], t.name, j))
     for K in q.kernels:
+        if K.byte_cols:
+            L.append("    unsigned %s_bo;  // byte-row staging buffers: offset in dynamic shared memory" % K.name)
         if K.pipe_mode() == "tma":
             L.append("    unsigned %s_ro; int %s_rs;  // column tile ring: byte offset in dynamic shared memory, stages" % (K.name, K.name))
-    L.append("    double* sc; double* part; unsigned* cnt;")
+    L.append("    double* sc; double* part; unsigned* cnt; unsigned long long* tcount;")
     for i in range(len(q.npart)):
         L.append("    long long part_off%d;" % i)
     L.append("    unsigned long long* res_count; long long res_cap;")
@@ -1695,27 +1777,32 @@ def render_query(q):
     for i in range(len(q.consts)):
         L.append("    c.k%d = a->consts[%d];" % (i, i))
     nt = len(q.tables)
-    L.append("    unsigned long long ff_off[%d], ff_len[%d];" % (max(1, nt), max(1, nt)))
+    L.append("    sdqlhost::TblRegion tr[%d];" % max(1, nt))
     for ti, t in enumerate(q.tables):
         P = len(t.parts)
         if P == 0:
             raise CodegenError("%s: table %s was never keyed" % (n, t.name))
+        t.index = ti
         mns = ", ".join(_stats_exprs(s)[0] for s in t.parts)
         rgs = ", ".join(_stats_exprs(s)[1] for s in t.parts)
         src = "c.n_%s" % t.src[1] if t.src[0] == "rel" else "c.%s.cap" % t.src[1].name
+        nf = len(t.fields)
         L.append("    {")
         L.append("        long long mn[%d] = {%s}, rng[%d] = {%s};" % (P, mns, P, rgs))
-        L.append("        unsigned long long u0 = ar.used;")
-        L.append("        if (!sdqlhost::size_table(&c.%s, %d, mn, rng, %s, c.%s_mn, c.%s_rng, c.%s_mul, ar))" %
-                 (t.name, P, src, t.name, t.name, t.name))
+        L.append("        void* ag[%d] = {nullptr};" % max(1, nf))
+        # presence bits in front of tables that are probed and built selectively (predicates in front of the build)
+        t.want_bits = bool(t.probed and t.builder is not None and t.builder.counted and BITS_FILTER)
+        L.append("        if (!sdqlhost::size_table(&c.%s, %d, mn, rng, %s, c.%s_mn, c.%s_rng, c.%s_mul, ar, &tr[%d], %d, ag, %s))" %
+                 (t.name, P, src, t.name, t.name, t.name, ti, nf, "true" if t.want_bits else "false"))
         L.append("            return sdqlhost::fail(SDQLB200_E_ARG, \"%s: key domain of %s does not fit 63 bits\");" % (n, t.name))
-        L.append("        ff_off[%d] = u0; ff_len[%d] = ar.used - u0;" % (ti, ti))
         for j, (_, ct) in enumerate(t.fields):
-            L.append("        c.%s_a%d = ar.alloc<%s>(c.%s.cap);" % (t.name, j, CT[ct], t.name))
+            L.append("        c.%s_a%d = (%s*)ag[%d];" % (t.name, j, CT[ct], j))
         L.append("    }")
     for t in q.tables:
         L.append("    int* own_%s = a->merge ? ar.alloc<int>(c.%s.cap) : nullptr;" % (t.name, t.name))
-    L.append("    c.sc = ar.alloc<double>(%d); c.cnt = ar.alloc<unsigned>(%d);" % (max(1, q.nsc), max(1, q.ncnt)))
+    L.append("    const unsigned long long tail_off = ar.used;  // scalars, counters, partials: zeroed before every run")
+    L.append("    c.sc = ar.alloc<double>(%d); c.cnt = ar.alloc<unsigned>(%d); c.tcount = ar.alloc<unsigned long long>(%d);" %
+             (max(1, q.nsc), max(1, q.ncnt), max(1, q.ntcount)))
     # launch plans: aggregation tier, shared memory (tier table + column tile ring), resident CTAs per SM, grid
     for K in q.kernels:
         if K.src[0] == "rel":
@@ -1735,8 +1822,13 @@ def render_query(q):
                      (tn, nf, K.name, K.name, nf))
             fn = "(tier_%s == 0 ? (const void*)%s<0> : tier_%s == 1 ? (const void*)%s<1> : (const void*)%s<2>)" % (
                 K.name, K.name, K.name, K.name, K.name)
+        elif K.templated:
+            fn = "(const void*)%s<2>" % K.name
         else:
             fn = "(const void*)%s" % K.name
+        if K.byte_cols:
+            L.append("        c.%s_bo = (unsigned)((sm_%s + 15) & ~(size_t)15); sm_%s = c.%s_bo + %du;" %
+                     (K.name, K.name, K.name, K.name, 1024 * sum(K.byte_cols.values())))
         if ring:
             widths = " + ".join({"i32": "4", "f64": "8", "code": "(size_t)a->cols[%d].width" % idx}[rep]
                                 for (col, rep), (arr, idx) in K.scan_cols.items())
@@ -1769,23 +1861,83 @@ def render_query(q):
     L.append("    if (!ar.ok()) return sdqlhost::fail(SDQLB200_E_WORKSPACE, \"%s: workspace of %%llu bytes needed\", ar.used);" % n)
     L.append("    cudaStream_t st = (cudaStream_t)a->stream;")
     L.append("    SDQL_CUDA(cudaEventRecord(sdqlhost_ev(0), st));")
-    L.append("    SDQL_CUDA(cudaMemsetAsync(a->workspace, 0, zero_end, st));")
-    for ti in range(nt):
-        L.append("    SDQL_CUDA(cudaMemsetAsync((char*)a->workspace + ff_off[%d], 0xFF, ff_len[%d], st));" % (ti, ti))
-    L.append("    int launches = 0; const bool kt = (a->flags & SDQLB200_F_KERNEL_TIMES) != 0;")
     L.append("    const unsigned pm = a->merge ? a->part_mask : 0u;  // multi-GPU: which relation arguments are partitioned")
     for t in q.tables:
         L.append("    bool part_%s = false;" % t.name)
     for K in q.kernels:
         if K.src[0] == "rel":
             L.append("    const bool part_%s = (pm >> %d) & 1u;" % (K.name, q.args.index(K.src[1])))
+    # cardinality passes: a kernel with predicates in front of a table build first counts the rows that reach the build,
+    # when its tables are big enough for their size to matter (or always when the count has to agree across ranks)
+    owned = {}
+    for t in q.tables:
+        owned.setdefault(t.builder, []).append(t)
+    for K in q.kernels:
+        K.count_ok = bool(K.counted and K.pipe_mode() != "tma" and owned.get(K))
+        if K.count_ok:
+            tot = " + ".join("tr[%d].len" % t.index for t in owned[K])
+            # worth it only when initialising / probing the worst-case tables costs clearly more than scanning the
+            # predicate columns a second time
+            if K.src[0] == "rel":
+                pb = sum({"i32": 4, "f64": 8, "code": 1}[rep] for (_, rep) in (K.pred_cols or ())) + sum(K.byte_cols.values())
+                scan = "(unsigned long long)c.n_%s * %dull" % (K.src[1], max(4, pb))
+            else:
+                scan = "(unsigned long long)c.%s.cap * 12ull" % K.src[1].name
+            L.append("    const bool cnt_%s = (%s) >= sdqlhost::count_min_bytes() && (%s) >= sdqlhost::count_min_ratio() * (%s);" %
+                     (K.name, tot, tot, scan))
+    for t in q.tables:
+        K = t.builder
+        guard = "if (!cnt_%s) " % K.name if (K is not None and K.count_ok) else ""
+        L.append("    %sSDQL_CUDA(sdqlhost_init_table(a->workspace, tr[%d], st));" % (guard, t.index))
+    L.append("    SDQL_CUDA(cudaMemsetAsync((char*)a->workspace + tail_off, 0, zero_end - tail_off, st));")
+    L.append("    int launches = 0; const bool kt = (a->flags & SDQLB200_F_KERNEL_TIMES) != 0;")
     L.append("    if (kt) SDQL_CUDA(cudaEventRecord(sdqlhost_kev(0), st));")
     for K in q.kernels:
-        if K.tiered:
-            L.append("    if (tier_%s == 0) SDQL_LAUNCH(%s<0>, g_%s, sdqlrt::kBlock, sm_%s, st, c);" % (K.name, K.name, K.name, K.name))
-            L.append("    else if (tier_%s == 1) SDQL_LAUNCH(%s<1>, g_%s, sdqlrt::kBlock, sm_%s, st, c);" % (K.name, K.name, K.name, K.name))
-            L.append("    else SDQL_LAUNCH(%s<2>, g_%s, sdqlrt::kBlock, sm_%s, st, c);" % (K.name, K.name, K.name))
-            L.append("    a->tier = tier_%s;" % K.name)
+        if K.src[0] == "tbl":  # the source table may have been right-sized since the launch plan was made
+            L.append("    { const int g2 = sdqlhost::grid_for(c.%s.cap, 8, sms); if (g2 < g_%s) g_%s = g2; }" %
+                     (K.src[1].name, K.name, K.name))
+        bits_tabs = [t for t in owned.get(K, []) if getattr(t, "want_bits", False)]
+        if K.count_ok or bits_tabs:
+            pe = part_expr(K)
+            cops = []
+            for t in owned[K]:
+                cops.append("(" + (" || ".join("((a->cols[%d].flags & SDQLB200_COL_PARTKEY) != 0)" % p_[1] for p_ in t.parts if p_[0] == "col") or "false") + ")")
+            L.append("    // partial tables that are merged across ranks keep the worst-case plan (all ranks must agree on it) and get")
+            L.append("    // no presence filter (the merge adds keys behind its back)")
+            L.append("    const bool merged_%s = a->merge != nullptr && %s && !(%s);" % (K.name, pe, " && ".join(cops)))
+            for t in bits_tabs:
+                L.append("    if (merged_%s) c.%s.bits = nullptr;" % (K.name, t.name))
+        if K.count_ok:
+            L.append("    if (cnt_%s) {" % K.name)
+            L.append("        const bool merged_ = merged_%s;" % K.name)
+            L.append("        if (!merged_) {")
+            if K.byte_cols:
+                L.append("            sdqlhost_occupancy((const void*)%s<3>, sm_%s);  // raises the dynamic shared memory limit" % (K.name, K.name))
+            L.append("            SDQL_LAUNCH(%s<3>, g_%s, sdqlrt::kBlock, %s, st, c);" % (K.name, K.name, "sm_%s" % K.name if K.byte_cols else "0"))
+            L.append("            SDQL_CUDA(cudaGetLastError());")
+            L.append("            unsigned long long h_cnt = 0;")
+            L.append("            SDQL_CUDA(cudaMemcpyAsync(&h_cnt, c.tcount + %d, 8, cudaMemcpyDeviceToHost, st));" % K.count_slot)
+            L.append("            SDQL_CUDA(cudaStreamSynchronize(st));")
+            for t in owned[K]:
+                nf = len(t.fields)
+                L.append("            {")
+                L.append("                void* ag[%d] = {%s};" % (max(1, nf), ", ".join("c.%s_a%d" % (t.name, j) for j in range(nf)) or "nullptr"))
+                L.append("                sdqlhost::replan_table(&c.%s, (char*)a->workspace, &tr[%d], (long long)h_cnt, ag);" % (t.name, t.index))
+                for j, (_, ct) in enumerate(t.fields):
+                    L.append("                c.%s_a%d = (%s*)ag[%d];" % (t.name, j, CT[ct], j))
+                L.append("            }")
+            L.append("        }")
+            for t in owned[K]:
+                L.append("        SDQL_CUDA(sdqlhost_init_table(a->workspace, tr[%d], st));" % t.index)
+            L.append("    }")
+        if K.templated:
+            if K.tiered:
+                L.append("    if (tier_%s == 0) SDQL_LAUNCH(%s<0>, g_%s, sdqlrt::kBlock, sm_%s, st, c);" % (K.name, K.name, K.name, K.name))
+                L.append("    else if (tier_%s == 1) SDQL_LAUNCH(%s<1>, g_%s, sdqlrt::kBlock, sm_%s, st, c);" % (K.name, K.name, K.name, K.name))
+                L.append("    else SDQL_LAUNCH(%s<2>, g_%s, sdqlrt::kBlock, sm_%s, st, c);" % (K.name, K.name, K.name))
+                L.append("    a->tier = tier_%s;" % K.name)
+            else:
+                L.append("    SDQL_LAUNCH(%s<2>, g_%s, sdqlrt::kBlock, sm_%s, st, c);" % (K.name, K.name, K.name))
         else:
             L.append("    SDQL_LAUNCH(%s, g_%s, sdqlrt::kBlock, sm_%s, st, c);" % (K.name, K.name, K.name))
         L.append("    SDQL_CUDA(cudaGetLastError()); ++launches;")
@@ -1851,6 +2003,13 @@ static int sdqlhost_sms() {
     return sms;
 }
 #endif
+
+// fill a dictionary's key / representative arrays with 0xFF (free) and zero its aggregate arrays
+static cudaError_t sdqlhost_init_table(void* ws, const sdqlhost::TblRegion& r, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync((char*)ws + r.off, 0xFF, r.ff_len, st);
+    if (e == cudaSuccess && r.z_len) e = cudaMemsetAsync((char*)ws + r.off + r.ff_len, 0, r.z_len, st);
+    return e;
+}
 
 // copy the result rows to host buffers (after the query's kernels).  The row counter sits directly in front of the
 // result columns in the arena, so a small result (the common case: aggregates) is one D2H copy into a pinned staging

@@ -43,14 +43,69 @@ struct Arena {
     bool ok() const { return base && used <= cap; }
 };
 
-struct TblPlan {
-    long long ff_off, ff_bytes;  // region to fill with 0xFF (rep, keys)
+// One dictionary's place in the workspace: the region reserved for it by the dry run (worst case: every source row
+// produces a distinct key) and the arrays currently laid out at the start of that region.
+struct TblRegion {
+    unsigned long long off, len;        // reserved bytes in the arena
+    unsigned long long ff_len;          // [off, off + ff_len): keys + rep, to be filled with 0xFF before the build
+    unsigned long long z_len;           // [off + ff_len, off + ff_len + z_len): aggregate arrays, to be zeroed
+    long double dom;                    // size of the packed key domain (9e18 = unbounded)
+    int nf;                             // aggregate fields (8 bytes per slot each)
+    unsigned long long bdom, bmod;      // presence filter: bits (0 = none) and modulus of the packed key (0 = whole key)
 };
 
-// Decide direct vs hash and allocate.  parts: value ranges [mn, mn+rng) of the by-value key parts.
+// a table smaller than this needs no presence filter in front (it is cache resident itself)
+static inline unsigned long long bits_min_bytes() {
+    static long long v = -1;
+    if (v < 0) { const char* e = getenv("SDQLB200_BITS_MIN_BYTES"); v = e ? atoll(e) : (4ll << 20); if (v < 0) v = 0; }
+    return (unsigned long long)v;
+}
+
+static inline unsigned long long up256(unsigned long long b) { return (b + 255) & ~255ull; }
+
+// direct vs hash for `rows` distinct keys at most.  Direct when the dense array is not (much) bigger than what a hash
+// table for `rows` keys would need.  SDQLB200_FORCE_HASH=1 (debug knob): never direct -- exercises the hash build /
+// probe / merge paths at small scale.
+static inline void plan_table(long double dom, long long rows, int* direct, long long* cap) {
+    static const bool force_hash = getenv("SDQLB200_FORCE_HASH") && getenv("SDQLB200_FORCE_HASH")[0] == '1';
+    if (rows < 1) rows = 1;
+    const long long domain = (long long)dom;
+    *direct = (!force_hash && dom <= (long double)(8 * rows + 65536) && domain < (1ll << 31)) ? 1 : 0;
+    if (*direct) { *cap = domain; return; }
+    const long long need = rows < domain ? rows : domain;
+    long long c = 1024;
+    while (c < 2 * need) c <<= 1;
+    *cap = c;
+}
+static inline unsigned long long table_bytes(int direct, long long cap, int nf) {
+    const unsigned long long n = (unsigned long long)(cap > 0 ? cap : 1);
+    return (direct ? 0 : up256(n * 8)) + up256(n * 4) + (unsigned long long)nf * up256(n * 8);
+}
+static inline unsigned long long bits_bytes(unsigned long long bdom) { return bdom ? up256(((bdom + 31) / 32) * 4) : 0; }
+// lay the table's arrays out at the start of its region: [keys (hash only)] [rep] [agg 0] .. [agg nf-1]
+static inline void place_table(sdqlrt::Tbl* t, char* base, TblRegion* r, void** aggs) {
+    const unsigned long long n = (unsigned long long)(t->cap > 0 ? t->cap : 1);
+    unsigned long long o = r->off;
+    t->keys = nullptr;
+    if (!t->direct) { t->keys = base ? (sdqlrt::u64*)(base + o) : nullptr; o += up256(n * 8); }
+    t->rep = base ? (int*)(base + o) : nullptr;
+    o += up256(n * 4);
+    r->ff_len = o - r->off;
+    for (int j = 0; j < r->nf; ++j) { aggs[j] = base ? (void*)(base + o) : nullptr; o += up256(n * 8); }
+    t->bits = nullptr;
+    t->bmod = r->bmod;
+    if (r->bdom && o - r->off >= bits_min_bytes()) {  // big table: presence bits in front of it
+        t->bits = base ? (unsigned*)(base + o) : nullptr;
+        o += bits_bytes(r->bdom);
+    }
+    r->z_len = o - r->off - r->ff_len;
+}
+
+// Decide direct vs hash and reserve the table's region.  parts: value ranges [mn, mn+rng) of the by-value key parts.
 // src_rows bounds the number of distinct keys.  Returns false if the key domain cannot be packed in 63 bits.
 static inline bool size_table(sdqlrt::Tbl* t, int nparts, const long long* mn, const long long* rng,
-                              long long src_rows, long long* o_mn, long long* o_rng, long long* o_mul, Arena& ar) {
+                              long long src_rows, long long* o_mn, long long* o_rng, long long* o_mul, Arena& ar,
+                              TblRegion* r, int nf, void** aggs, bool want_bits) {
     long double dom = 1;
     long long mul = 1;
     for (int j = 0; j < nparts; ++j) {
@@ -70,25 +125,50 @@ static inline bool size_table(sdqlrt::Tbl* t, int nparts, const long long* mn, c
         }
         mul *= o_rng[j];
     }
-    if (src_rows < 1) src_rows = 1;
-    long long domain = (long long)dom;
-    // direct when the dense array is not (much) bigger than what a hash table for src_rows keys would need.
-    // SDQLB200_FORCE_HASH=1 (debug knob): never direct -- exercises the hash build / probe / merge paths at small scale
-    static const bool force_hash = getenv("SDQLB200_FORCE_HASH") && getenv("SDQLB200_FORCE_HASH")[0] == '1';
-    bool direct = !force_hash && dom <= (long double)(8 * src_rows + 65536) && domain < (1ll << 31);
-    t->direct = direct ? 1 : 0;
-    if (direct) {
-        t->cap = domain;
-        t->keys = nullptr;
-    } else {
-        long long need = src_rows < domain ? src_rows : domain;
-        long long cap = 1024;
-        while (cap < 2 * need) cap <<= 1;
-        t->cap = cap;
-        t->keys = ar.alloc<sdqlrt::u64>(cap);
+    plan_table(dom, src_rows, &t->direct, &t->cap);
+    r->dom = dom;
+    r->nf = nf;
+    r->bdom = r->bmod = 0;
+    if (want_bits) {  // one bit per packed key if that is at most 2^31 bits (256 MB), else one per value of the first part
+        const long double lim = 2147483648.0L;
+        // SDQLB200_BITS_PREFIX=1 (debug knob): composite keys always get the first-part filter (exercised at small scale)
+        static const bool force_prefix = getenv("SDQLB200_BITS_PREFIX") && getenv("SDQLB200_BITS_PREFIX")[0] == '1';
+        if (dom <= lim && !(force_prefix && nparts > 1)) r->bdom = (unsigned long long)dom;
+        else if (nparts > 1 && o_rng[0] > 0 && (long double)o_rng[0] <= lim) { r->bdom = (unsigned long long)o_rng[0]; r->bmod = r->bdom; }
     }
-    t->rep = ar.alloc<int>(t->cap);
+    r->off = ar.used;
+    r->len = table_bytes(t->direct, t->cap, nf) + bits_bytes(r->bdom);
+    ar.alloc<char>((long long)r->len);
+    place_table(t, ar.ok() ? ar.base : nullptr, r, aggs);
     return true;
+}
+
+// Right-size a table once the number of rows that reach its build is known (cardinality pass): same region, smaller
+// (cache-resident) arrays.  Keeps the worst-case plan when the new one would not fit the reservation.
+static inline bool replan_table(sdqlrt::Tbl* t, char* base, TblRegion* r, long long rows, void** aggs) {
+    int direct;
+    long long cap;
+    plan_table(r->dom, rows, &direct, &cap);
+    if (table_bytes(direct, cap, r->nf) + bits_bytes(r->bdom) > r->len) return false;
+    if (direct == t->direct && cap == t->cap) return false;
+    t->direct = direct;
+    t->cap = cap;
+    place_table(t, base, r, aggs);
+    return true;
+}
+
+// tables whose reservation is at least this big get a cardinality pass before they are built
+static inline unsigned long long count_min_bytes() {
+    static long long v = -1;
+    if (v < 0) { const char* e = getenv("SDQLB200_COUNT_MIN_BYTES"); v = e ? atoll(e) : (8ll << 20); if (v < 0) v = 0; }
+    return (unsigned long long)v;
+}
+
+// ... and whose reservation is at least this many times the bytes the cardinality pass has to scan
+static inline unsigned long long count_min_ratio() {
+    static long long v = -1;
+    if (v < 0) { const char* e = getenv("SDQLB200_COUNT_MIN_RATIO"); v = e ? atoll(e) : 2; if (v < 0) v = 0; }
+    return (unsigned long long)v;
 }
 
 // Column tile ring (generated rel-scan kernels, "tma" pipeline): pick the number of stages and the CTAs per SM the

@@ -36,6 +36,12 @@ typedef long long i64;
 
 constexpr int kBlock = 256;   // threads per CTA for every generated kernel
 constexpr int kVec = 4;       // rows per thread per iteration
+#ifndef SDQLB200_EMU
+constexpr int kLanes = 32;    // threads that share one byte-row staging buffer (a warp)
+#else
+constexpr int kLanes = 1;
+#endif
+constexpr int kStageRows = kLanes * kVec;  // rows one warp stages per iteration
 constexpr u64 kEmpty = ~0ull;
 
 // ---------------------------------------------------------------------------------------------
@@ -97,6 +103,35 @@ SDQL_DEV void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long
 }
 #endif
 
+// ---------------------------------------------------------------------------------------------
+// byte-row staging: the rows of a fixed-width string column that a warp is about to examine (kLanes x kVec consecutive
+// rows = one contiguous run of bytes) are copied into the warp's shared-memory buffer with coalesced 128-bit loads, so
+// the per-row character loops read shared memory (row strides are odd multiples of 4 bytes for odd widths: conflict
+// free) instead of issuing one uncoalesced global byte load per character.  All lanes of the warp must call.
+// ---------------------------------------------------------------------------------------------
+SDQL_DEV void stage_rows(unsigned char* dst, const unsigned char* col, i64 row0, i64 n, int W) {
+    const i64 r1 = row0 + kStageRows < n ? row0 + kStageRows : n;
+#ifndef SDQLB200_EMU
+    __syncwarp();  // the previous iteration's readers are done with the buffer
+    if (r1 > row0) {
+        const size_t bytes = (size_t)(r1 - row0) * (size_t)W;
+        const unsigned char* src = col + row0 * W;  // 16-byte aligned: row0 is a multiple of 128, the column base of 256
+        const int lane = threadIdx.x & 31;
+        const size_t nv = bytes >> 4;
+        for (size_t k = lane; k < nv; k += 32) {
+            uint4 v;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"((const uint4*)src + k));
+            ((uint4*)dst)[k] = v;
+        }
+        for (size_t k = (nv << 4) + lane; k < bytes; k += 32) dst[k] = ld1(src + k);
+    }
+    __syncwarp();
+#else
+    if (r1 > row0) memcpy(dst, col + row0 * W, (size_t)(r1 - row0) * (size_t)W);
+#endif
+}
+
 // dictionary-code columns are uint8 when the dictionary has <= 256 entries, int32 otherwise (uniform branch)
 SDQL_DEV void ld4_code(const void* p, i64 i0, int width, int (&v)[4]) {
     if (width == 1) ld4((const unsigned char*)p + i0, v);
@@ -115,7 +150,23 @@ struct Tbl {
                  // after a cross-GPU merge: -2 = present but owned (iterated, late-materialised) by another rank
     i64 cap;     // slots (direct: key domain size; hash: power of two)
     int direct;  // 1: slot == packed key
+    // presence filter in front of selective tables: one bit per value of the packed key (bmod == 0) or of its first part
+    // (bmod = that part's range: mixed-radix packing puts it in the low digits).  nullptr = no filter.
+    unsigned* bits;
+    u64 bmod;
 };
+
+SDQL_DEV bool tbl_maybe(const Tbl& t, u64 key) {
+    if (!t.bits) return true;
+    const u64 b = t.bmod ? key % t.bmod : key;
+    return (ld1(t.bits + (b >> 5)) >> (unsigned)(b & 31)) & 1u;
+}
+SDQL_DEV void tbl_mark(const Tbl& t, u64 key) {
+    if (!t.bits) return;
+    const u64 b = t.bmod ? key % t.bmod : key;
+    const unsigned m = 1u << (unsigned)(b & 31);
+    if (!(t.bits[b >> 5] & m)) atomicOr(t.bits + (b >> 5), m);
+}
 
 SDQL_DEV u64 hash64(u64 x) {  // splitmix64 finaliser
     x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
@@ -124,7 +175,7 @@ SDQL_DEV u64 hash64(u64 x) {  // splitmix64 finaliser
 
 // -> slot or -1.  `ok` = every key part was inside the table's packing range.
 SDQL_DEV int tbl_find(const Tbl& t, u64 key, bool ok) {
-    if (!ok) return -1;
+    if (!ok || !tbl_maybe(t, key)) return -1;
     if (t.direct) return ld1(t.rep + key) != -1 ? (int)key : -1;  // -2 = present, owned by another rank
     u64 m = (u64)t.cap - 1, h = hash64(key) & m;
     for (;;) {
@@ -141,6 +192,7 @@ SDQL_DEV int tbl_upsert(const Tbl& t, u64 key, int src, bool& is_new) {
         int old = t.rep[key];
         if (old < 0) old = atomicCAS(t.rep + key, -1, src);
         is_new = old < 0;
+        if (is_new) tbl_mark(t, key);
         return (int)key;
     }
     u64 m = (u64)t.cap - 1, h = hash64(key) & m;
@@ -149,7 +201,7 @@ SDQL_DEV int tbl_upsert(const Tbl& t, u64 key, int src, bool& is_new) {
         if (k == key) { is_new = false; return (int)h; }
         if (k == kEmpty) {
             u64 prev = atomicCAS(t.keys + h, kEmpty, key);
-            if (prev == kEmpty) { t.rep[h] = src; is_new = true; return (int)h; }
+            if (prev == kEmpty) { t.rep[h] = src; is_new = true; tbl_mark(t, key); return (int)h; }
             if (prev == key) { is_new = false; return (int)h; }
         }
         h = (h + 1) & m;
@@ -344,12 +396,17 @@ SDQL_DEV int str_len(const unsigned char* s, int w) {
     return n;
 }
 // first index of pat in s, -1 if absent (varchar.h:91-97 firstIndex -> wcsstr, which stops at the first NUL)
+// single pass: a match cannot start at or span a NUL (patterns contain none), so the scan simply stops at the first NUL
 SDQL_DEV int str_find(const unsigned char* s, int w, const char* pat, int plen) {
-    int n = str_len(s, w);
-    for (int i = 0; i + plen <= n; ++i) {
-        int j = 0;
-        while (j < plen && s[i + j] == (unsigned char)pat[j]) ++j;
-        if (j == plen) return i;
+    const unsigned char p0 = (unsigned char)pat[0];
+    for (int i = 0; i + plen <= w; ++i) {
+        const unsigned char ch = s[i];
+        if (ch == 0) return -1;
+        if (ch == p0) {
+            int j = 1;
+            while (j < plen && s[i + j] == (unsigned char)pat[j]) ++j;
+            if (j == plen) return i;
+        }
     }
     return -1;
 }

@@ -88,6 +88,41 @@ __global__ void __launch_bounds__(kBlock) k_fixed32(const int* __restrict__ src,
     }
 }
 
+// bit-packed columns: MODE 0 = table[code], 1 = (double)(base + code) / scale, 2 = (int)(base + code), 3 = (uint8)code
+template <class OUT, int MODE>
+__global__ void __launch_bounds__(kBlock) k_bits(const unsigned* __restrict__ src, OUT* __restrict__ dst, long long n,
+                                                 int nbits, const OUT* __restrict__ table, long long base, double scale) {
+    const unsigned mask = nbits >= 32 ? 0xffffffffu : ((1u << nbits) - 1u);
+    auto code_at = [&](long long i) -> unsigned {
+        const long long bit = i * nbits;
+        const long long w = bit >> 5;
+        const unsigned lo = __ldg(src + w), hi = __ldg(src + w + 1);  // neighbours share words: L1-cached loads
+        return __funnelshift_r(lo, hi, (unsigned)(bit & 31)) & mask;
+    };
+    auto value = [&](unsigned c) -> OUT {
+        if (MODE == 0) return __ldg(table + c);
+        if (MODE == 1) return (OUT)((double)(base + (long long)c) / scale);
+        if (MODE == 2) return (OUT)(base + (long long)c);
+        return (OUT)c;
+    };
+    const long long ngrp = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ngrp; g += stride) {
+        const long long i = g << 2;
+        const OUT a = value(code_at(i)), b = value(code_at(i + 1)), c = value(code_at(i + 2)), d = value(code_at(i + 3));
+        if constexpr (sizeof(OUT) == 1) {
+            const unsigned w = (unsigned)a | ((unsigned)b << 8) | ((unsigned)c << 16) | ((unsigned)d << 24);
+            asm volatile("st.global.u32 [%0], %1;" ::"l"(dst + i), "r"(w) : "memory");
+        } else {
+            st4(dst + i, a, b, c, d);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const long long i = (ngrp << 2) + threadIdx.x;
+        dst[i] = value(code_at(i));
+    }
+}
+
 int grid_for(long long groups) {
     static int sms = 0;
     if (!sms) {
@@ -112,13 +147,16 @@ int32_t sdqlb200_wire_src_width(int32_t kind) {
         case SDQLB200_WIRE_DICT16_F64: case SDQLB200_WIRE_DICT16_I32: return 2;
         case SDQLB200_WIRE_FIXED32_F64: return 4;
     }
-    return 0;
+    return 0;  // unknown, or bit-packed (nbits / 8 bytes per element)
 }
 
 int32_t sdqlb200_wire_dst_width(int32_t kind) {
     switch (kind) {
         case SDQLB200_WIRE_DICT8_F64: case SDQLB200_WIRE_DICT16_F64: case SDQLB200_WIRE_FIXED32_F64: return 8;
         case SDQLB200_WIRE_DICT8_I32: case SDQLB200_WIRE_DICT16_I32: return 4;
+        case SDQLB200_WIRE_BITS_DICT_F64: case SDQLB200_WIRE_BITS_FIXED_F64: return 8;
+        case SDQLB200_WIRE_BITS_DICT_I32: case SDQLB200_WIRE_BITS_I32: return 4;
+        case SDQLB200_WIRE_BITS_U8: return 1;
     }
     return 0;
 }
@@ -155,6 +193,43 @@ int sdqlb200_wire_decode(int32_t kind, const void* src, void* dst, int64_t rows,
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(SDQLB200_E_CUDA, "%s:%d: wire_decode launch: %s", __FILE__, __LINE__, cudaGetErrorString(e));
+    return SDQLB200_OK;
+}
+
+int sdqlb200_wire_decode_bits(int32_t kind, const void* src, void* dst, int64_t rows, int32_t nbits, const void* table,
+                              int64_t base, double scale, void* stream) {
+    if (kind < SDQLB200_WIRE_BITS_DICT_F64 || kind >= SDQLB200_WIRE_ALL_KINDS)
+        return fail(SDQLB200_E_ARG, "wire_decode_bits: kind %d is not bit-packed", kind);
+    if (nbits < 1 || nbits > 32) return fail(SDQLB200_E_ARG, "wire_decode_bits: nbits %d outside 1..32", nbits);
+    if (rows < 0 || (rows > 0 && (!src || !dst))) return fail(SDQLB200_E_ARG, "wire_decode_bits: null buffer");
+    if (((uintptr_t)src | (uintptr_t)dst) & 15) return fail(SDQLB200_E_ARG, "wire_decode_bits: buffers must be 16-byte aligned");
+    const bool dict = kind == SDQLB200_WIRE_BITS_DICT_F64 || kind == SDQLB200_WIRE_BITS_DICT_I32;
+    if (dict && !table) return fail(SDQLB200_E_ARG, "wire_decode_bits: dictionary kinds need a device table");
+    if (kind == SDQLB200_WIRE_BITS_FIXED_F64 && !(scale > 0)) return fail(SDQLB200_E_ARG, "wire_decode_bits: scale must be positive");
+    if (kind == SDQLB200_WIRE_BITS_U8 && nbits > 8) return fail(SDQLB200_E_ARG, "wire_decode_bits: uint8 codes have at most 8 bits");
+    if (rows == 0) return SDQLB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for((rows + 3) / 4);
+    const unsigned* s32 = (const unsigned*)src;
+    switch (kind) {
+        case SDQLB200_WIRE_BITS_DICT_F64:
+            k_bits<double, 0><<<grid, kBlock, 0, st>>>(s32, (double*)dst, rows, nbits, (const double*)table, 0, 1.0);
+            break;
+        case SDQLB200_WIRE_BITS_DICT_I32:
+            k_bits<int, 0><<<grid, kBlock, 0, st>>>(s32, (int*)dst, rows, nbits, (const int*)table, 0, 1.0);
+            break;
+        case SDQLB200_WIRE_BITS_FIXED_F64:
+            k_bits<double, 1><<<grid, kBlock, 0, st>>>(s32, (double*)dst, rows, nbits, nullptr, base, scale);
+            break;
+        case SDQLB200_WIRE_BITS_I32:
+            k_bits<int, 2><<<grid, kBlock, 0, st>>>(s32, (int*)dst, rows, nbits, nullptr, base, 1.0);
+            break;
+        case SDQLB200_WIRE_BITS_U8:
+            k_bits<unsigned char, 3><<<grid, kBlock, 0, st>>>(s32, (unsigned char*)dst, rows, nbits, nullptr, 0, 1.0);
+            break;
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SDQLB200_E_CUDA, "%s:%d: wire_decode_bits launch: %s", __FILE__, __LINE__, cudaGetErrorString(e));
     return SDQLB200_OK;
 }
 

@@ -227,8 +227,8 @@ class ColumnStore:
             # the column crosses the link in its packed form and is expanded on the device (csrc/sdqlb200_wire.cu)
             ptr, holder, h2d = backend().upload_packed(packed)
             self.h2d_bytes += h2d
-            col = DeviceColumn(rep, ptr, holder, packed.rows, packed.min, packed.max, 4 if rep == "i32" else 8, None,
-                               packed.rows * (4 if rep == "i32" else 8))
+            w = {"i32": 4, "f64": 8, "code": 1}[rep]
+            col = DeviceColumn(rep, ptr, holder, packed.rows, packed.min, packed.max, w, packed.dictionary, packed.rows * w)
         else:
             img, mn, mx, w, d = _encode(src, rep, width)
             ptr, holder = backend().upload(img)

@@ -58,3 +58,43 @@ def test_empty_relation(emu_module):
             cols.append(Column(c, "i32", np.zeros(0, dtype=np.int32)))
     assert emu_module.run("q6", [cols]) == 0.0
     assert emu_module.run("q1", [cols]).size() == 0
+
+
+FORCED = {"SDQLB200_COUNT_MIN_BYTES": "0", "SDQLB200_COUNT_MIN_RATIO": "0", "SDQLB200_BITS_MIN_BYTES": "0"}
+
+
+@pytest.fixture(scope="module", params=["full_key_bits", "prefix_bits", "hash_tables"])
+def forced_module(request, tmp_path_factory):
+    """the same module with every optional table path switched on at tiny scale: cardinality passes in front of every
+    selective build (right-sized tables), presence filters in front of every probed table (whole-key and first-part
+    variants), and hash tables everywhere (no direct indexing).  The knobs are read once per loaded library."""
+    env = dict(FORCED)
+    if request.param == "prefix_bits":
+        env["SDQLB200_BITS_PREFIX"] = "1"
+    if request.param == "hash_tables":
+        env["SDQLB200_FORCE_HASH"] = "1"
+    old_env = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    d = tmp_path_factory.mktemp("emu_" + request.param)
+    text, _ = build.compile_source(open(QUERY_SCRIPT).read(), "queries.py")
+    cu = os.path.join(d, "q.cu")
+    open(cu, "w").write(text)
+    so = emu.build_emu(cu, os.path.join(d, "q_emu_%s.so" % request.param))
+    old = runtime._backend
+    runtime.set_backend(emu.EmuBackend())
+    runtime.STORE.clear()
+    yield runtime.CompiledModule(so)
+    runtime.set_backend(old)
+    runtime.STORE.clear()
+    for k, v in old_env.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+@pytest.mark.parametrize("q", QUERIES)
+def test_forced_table_paths_match_reference(forced_module, q):
+    gold = golden(0.01)
+    got = forced_module.run(q, compact_db(0.01, rr.QUERY_ARGS[q]))
+    assert compare(got, gold[q]) is None
