@@ -36,6 +36,10 @@ class CodegenError(Exception):
     pass
 
 
+class _SplitDone(Exception):
+    """unwinds run_body after the kernel body was split into a filter phase and a compacted phase"""
+
+
 # scan-loop latency hiding:
 #   "tma" = bulk-async (TMA engine) copies of whole column tiles into a multi-stage shared-memory ring tracked by
 #           mbarriers: bytes in flight = stages x tile, no registers held by outstanding loads
@@ -46,6 +50,10 @@ PF_DIST = int(os.environ.get("SDQLB200_PF_DIST", "2"))
 RING_ROWS_PER_THREAD = int(os.environ.get("SDQLB200_RING_ROWS", "0"))  # 0 = per kernel (Kernel.ring_rows)
 RING_MAX_ROW_BYTES = 100     # wider scans cannot keep two stages in 227 KB of shared memory: they use LDGs
 BYTE_STAGING = os.environ.get("SDQLB200_BYTE_STAGING", "1") != "0"  # string columns of the scanned row go through shared memory
+# measured on B200 (Q13, SF10): the word-wise search loses to the byte loop with look-ahead (every warp has some lane that
+# needs the per-character slow path), so it is opt-in
+STRFIND_W = os.environ.get("SDQLB200_STRFIND_W", "0") == "1"
+COMPACT = os.environ.get("SDQLB200_COMPACT", "1") != "0"  # rows surviving a selective probe are queued and re-dealt to all lanes
 BITS_FILTER = os.environ.get("SDQLB200_BITS", "1") != "0"  # presence bitmaps in front of selective, probed tables
 COUNT_PASS = os.environ.get("SDQLB200_COUNT_PASS", "1") != "0"  # cardinality passes in front of selective table builds
 
@@ -87,8 +95,9 @@ class SRec:
 class SRow:
     """record = row ``row`` of relation argument ``arg``."""
 
-    def __init__(self, q, arg, row, scan=False, prov=E, keycode=None, token=None):
+    def __init__(self, q, arg, row, scan=False, prov=E, keycode=None, token=None, gather=False):
         self.q, self.arg, self.row, self.scan, self.prov, self.keycode, self.token = q, arg, row, scan, prov, keycode, token
+        self.gather = gather  # the scanned row seen from another lane (hit compaction): values are loaded by row id
 
     def field(self, K, name):
         return self.q.col_value(K, self, name)
@@ -307,6 +316,8 @@ class Kernel:
         self.smem_expr = "0"
         self.tier_expr = "2"
         self.scan_var = "i"
+        self.body2 = None         # hit compaction: the full body re-evaluated for a queued row id `iq` (all lanes busy)
+        self.nprobe_sel = 0       # selective probes evaluated so far (lookups into tables built behind predicates)
         self.byte_cols = OrderedDict()  # input idx -> width: fixed-width string columns staged through shared memory
         self.counted = False      # has a cardinality-pass variant (TIER == 3): predicates in front of a table build
         self.pred_cols = None     # scan columns the predicates read (the only ones the cardinality pass loads)
@@ -403,7 +414,7 @@ class Kernel:
         tmpl = "template <int TIER>\n" if self.templated else ""
         L.append("%s__global__ void __launch_bounds__(sdqlrt::kBlock) %s(const __grid_constant__ %s_ctx c) {" %
                  (tmpl, self.name, q.name))
-        if self.tiered or self.pipe_mode() == "tma" or self.byte_cols:
+        if self.tiered or self.pipe_mode() == "tma" or self.byte_cols or self.body2 is not None:
             L.append("    SDQL_EXTERN_SMEM(sm);")
         L += ["    " + s for s in self.pre]
         if self.src[0] == "rel" and self.pipe_mode() == "tma":
@@ -445,23 +456,34 @@ class Kernel:
             L.append("    const long long gstride = (long long)gridDim.x * blockDim.x;")
             L.append("    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
             loop_cond = "g < ngrp"
+            if self.body2 is not None:
+                loop_cond = "g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp"
+                L.append("    int* const wq = (int*)((unsigned char*)sm + c.%s_qo) + (threadIdx.x / sdqlrt::kLanes) * sdqlrt::kQueueSlots;" % self.name)
+                L.append("    const int lane_ = (int)(threadIdx.x & (sdqlrt::kLanes - 1));")
+                L.append("    int wcnt = 0;  // rows queued by this warp (the same value in every lane)")
             if self.byte_cols:
                 # every lane of a warp runs the same number of iterations (the warp stages its rows cooperatively)
                 loop_cond = "g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp"
                 boff = 0
                 for idx, w in self.byte_cols.items():
                     L.append("    unsigned char* const bs%d = (unsigned char*)sm + c.%s_bo + %du + (threadIdx.x / sdqlrt::kLanes) * %du;" %
-                             (idx, self.name, boff, 128 * w))
+                             (idx, self.name, 16 + boff, 128 * w))
                     boff += 1024 * w
             stage = ["        sdqlrt::stage_rows(bs%d, c.in%d, (g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1))) << 2, n, %d);" % (idx, idx, w)
                      for idx, w in self.byte_cols.items()]
+
+            def loop_head(cond):
+                if self.body2 is None:
+                    return ["    while (%s) {" % cond]
+                # compaction: the drain below must also run once after the last scan iteration (one copy of the body)
+                return ["    for (;;) {", "    const bool more_ = %s;" % cond, "    if (more_) {"]
             pipe = self.pipe_mode() or "reg"
             if pipe == "reg":
                 for (col, rep), (arr, idx) in self.scan_cols.items():
                     L.append("    %s %s[4], %s[4];" % (ety[rep], arr, "q_" + arr[2:]))
                 L.append("    if (g < ngrp)")
                 L += loads("r_", "g", "    ")
-                L.append("    while (%s) {" % loop_cond)
+                L += loop_head(loop_cond)
                 L.append("        const long long gn = g + gstride;")
                 L.append("        if (gn < ngrp)")
                 L += loads("q_", "gn", "        ")
@@ -469,7 +491,7 @@ class Kernel:
             else:  # "l2": single register buffer, the group PF_DIST iterations ahead is prefetched into L2
                 for (col, rep), (arr, idx) in self.scan_cols.items():
                     L.append("    %s %s[4];" % (ety[rep], arr))
-                L.append("    while (%s) {" % loop_cond)
+                L += loop_head(loop_cond)
                 L.append("        const long long gn = g + gstride;")
                 L += stage
                 L.append("        { const long long gp = g + %d * gstride; if (gp < ngrp) {" % PF_DIST)
@@ -485,9 +507,17 @@ class Kernel:
             L.append("#pragma unroll")
             L.append("        for (int u = 0; u < 4; ++u) {")
             L.append("            const long long i = i0 + u;")
+            if self.body2 is not None:
+                L.append("            bool pass_ = false;")
             L.append("            if (i < n) {")
             L += ["                " + x for x in self.body]
             L.append("            }")
+            if self.body2 is not None:  # warp-aggregated push of the surviving row ids
+                L.append("            {")
+                L.append("                const unsigned m_ = sdqlrt::warp_ballot(pass_);")
+                L.append("                if (pass_) wq[wcnt + __popc(m_ & ((1u << lane_) - 1u))] = (int)i;")
+                L.append("                wcnt += __popc(m_);")
+                L.append("            }")
             L.append("        }")
             L.append("        g = gn;")
             if self.scan_cols and pipe == "reg":
@@ -497,6 +527,22 @@ class Kernel:
                     L.append("            %s[u] = %s[u];" % (arr, "q_" + arr[2:]))
                 L.append("        }")
             L.append("    }")
+            if self.body2 is not None:
+                # deal the queued rows to the lanes: full groups of 32 while the scan runs, the remainder after it
+                L.append("    for (;;) {")
+                L.append("        const int take_ = wcnt >= sdqlrt::kLanes ? sdqlrt::kLanes : (more_ ? 0 : wcnt);")
+                L.append("        if (take_ == 0) break;")
+                L.append("        wcnt -= take_;")
+                L.append("        sdqlrt::warp_sync();")
+                L.append("        const bool act_ = lane_ < take_;")
+                L.append("        const long long iq = act_ ? (long long)wq[wcnt + lane_] : 0ll;")
+                L.append("        sdqlrt::warp_sync();")
+                L.append("        if (act_) {")
+                L += ["            " + x for x in self.body2]
+                L.append("        }")
+                L.append("    }")
+                L.append("    if (!more_) break;")
+                L.append("    }")
         elif self.src[0] == "tbl":
             t = self.src[1]
             L.append("    const long long n = c.%s.cap;" % t.name)
@@ -915,7 +961,7 @@ class GroupSink(KeyedSink):
                     else:
                         P.append("        const long long v%d = sdqlrt::block_sum((long long)ra%d_%d);" % (j, j, sl_))
                 P.append("        if (threadIdx.x == 0 && r >= 0) {")
-                P.append("            atomicMax(c.%s.rep + %d, r); sdqlrt::tbl_mark(c.%s, %dull);" % (t.name, sl_, t.name, sl_))
+                P.append("            atomicMax(c.%s.rep + %d, r);" % (t.name, sl_))
                 for j, (_, ct) in enumerate(t.fields):
                     P.append("            sdqlrt::red_add(c.%s_a%d + %d, v%d);" % (t.name, j, sl_, j))
                 P.append("        }")
@@ -925,7 +971,7 @@ class GroupSink(KeyedSink):
             P.append("    for (long long k = threadIdx.x; k < ncap; k += blockDim.x) {")
             P.append("        int r = smrep[k];")
             P.append("        if (r >= 0) {")
-            P.append("            atomicMax(c.%s.rep + k, r); sdqlrt::tbl_mark(c.%s, (unsigned long long)k);" % (t.name, t.name))
+            P.append("            atomicMax(c.%s.rep + k, r);" % t.name)
             for j, (_, ct) in enumerate(t.fields):
                 if ct == "f64":
                     P.append("            sdqlrt::red_add(c.%s_a%d + k, __longlong_as_double(sm[k * %d + %d]));" % (t.name, j, nf, j))
@@ -1079,12 +1125,12 @@ class Query:
         on_scan = row.scan and K is not None and K.src == ("rel", row.arg)
         prov = row.prov if not on_scan else frozenset([("col", row.arg, col, "i")])
         if isinstance(kind, tuple):
-            s = SStr("ref", arg=row.arg, col=col, row=row.row, scan=on_scan, width=kind[1], prov=prov)
+            s = SStr("ref", arg=row.arg, col=col, row=row.row, scan=on_scan and not row.gather, width=kind[1], prov=prov)
             if row.keycode == ("ref", row.arg, col, row.row) and row.token is not None:
                 s.det = frozenset([row.token])
             return s
         rep = "f64" if kind == "float" else "i32"
-        if on_scan:
+        if on_scan and not row.gather:
             code = K.scan_col(col, rep)
         else:
             code = "sdqlrt::ld1(c.in%d + %s)" % (self.input(row.arg, col, rep), row.row)
@@ -1250,7 +1296,11 @@ class Query:
             elem = key
         env2 = dict(env)
         env2[S.varExpr.name] = elem
-        self.run_body(S.bodyExpr, env2, K)
+        K.root_body, K.root_env, K.row_var = S.bodyExpr, env2, S.varExpr.name
+        try:
+            self.run_body(S.bodyExpr, env2, K, chain=True)
+        except _SplitDone:
+            pass
         if K.sink is None:
             raise CodegenError("sum body never produces a value")
         out = K.sink.finish()
@@ -1277,7 +1327,24 @@ class Query:
             return ReduceSink(self, K, v)
         raise CodegenError("sum body produces unsupported value %s" % type(v).__name__)
 
-    def run_body(self, e, env, K):
+    def split_here(self, K):
+        """hit compaction: everything emitted so far (scan-row predicates up to and including a selective probe) becomes
+        the FILTER phase, which only queues the ids of surviving rows in the warp's shared-memory queue; the complete
+        body is then re-evaluated for a queued row id with all 32 lanes busy (a few percent of the rows survive such a
+        probe: without the queue the long dependent-load chains behind it run with one active lane per warp)."""
+        K.emit("pass_ = true;")
+        while K.depth > 0:
+            K.close()
+        body1, cse1 = K.body, K.cse
+        K.body, K.cse, K.depth = [], [{}], 0
+        K.scan_var = "iq"
+        env = dict(K.root_env)
+        env[K.row_var] = SPair(SRow(self, K.src[1], "iq", scan=True, gather=True), TRUE)
+        self.run_body(K.root_body, env, K, chain=False)
+        K.body2, K.body, K.cse = K.body, body1, cse1
+        raise _SplitDone()
+
+    def run_body(self, e, env, K, chain=False):
         if isinstance(e, ir.IfExpr):
             trivial_else = isinstance(e.elseBodyExpr, ir.EmptyDicConsExpr) or (
                 isinstance(e.elseBodyExpr, ir.ConstantExpr) and e.elseBodyExpr.value in (None, 0, 0.0, False))
@@ -1285,10 +1352,14 @@ class Query:
                 raise CodegenError("if/else with a non-zero else branch at statement level is not supported")
             n = 0
             for conj in and_chain(e.condExpr):
+                before = K.nprobe_sel
                 c = self.ev(conj, env, K)
                 K.open_if(as_bool(c))
                 n += 1
-            self.run_body(e.thenBodyExpr, env, K)
+                if (chain and COMPACT and K.nprobe_sel > before and K.body2 is None and K.src[0] == "rel"
+                        and PIPELINE != "tma" and K.sink is None):
+                    self.split_here(K)
+            self.run_body(e.thenBodyExpr, env, K, chain=chain)
             for _ in range(n):
                 K.close()
             return
@@ -1377,6 +1448,8 @@ class Query:
         if K is None:
             raise CodegenError("dictionary lookup outside of a sum body")
         t.probed = True
+        if t.builder is not None and t.builder.counted:
+            K.nprobe_sel += 1
         leaves = flatten(K, keyval)
         n_expected = len(t.parts) if t.inner is None else t.inner[0]
         # the probe key has the build key's *full* shape; keep the positions the build kept by value
@@ -1585,13 +1658,16 @@ class Query:
         if s == XF.StringContains:
             pat, subj = a, self.ev(e.inp3, env, K)
             ptr, w = self.str_ptr(K, subj)
-            return SScalar("bool", "(sdqlrt::str_find(%s, %d, %s, %d) >= 0)" % (ptr, w, cstr(pat.value), len(pat.value)), subj.prov)
+            fn = "str_find_w" if (ptr.startswith("(bs") and STRFIND_W) else "str_find"  # staged rows: word-wise search
+            return SScalar("bool", "(sdqlrt::%s(%s, %d, %s, %d) >= 0)" % (fn, ptr, w, cstr(pat.value), len(pat.value)), subj.prov)
         b = self.ev(e.inp2, env, K)
         if s in (XF.StartsWith, XF.EndsWith, XF.FirstIndex):
             if not (isinstance(b, SStr) and b.kind == "const"):
                 raise CodegenError("pattern must be a string constant")
             ptr, w = self.str_ptr(K, a)
             fn = {XF.StartsWith: "str_starts", XF.EndsWith: "str_ends", XF.FirstIndex: "str_find"}[s]
+            if fn == "str_find" and ptr.startswith("(bs") and STRFIND_W:
+                fn = "str_find_w"  # staged rows: word-wise search in shared memory
             code = "sdqlrt::%s(%s, %d, %s, %d)" % (fn, ptr, w, cstr(b.value), len(b.value))
             if s == XF.FirstIndex:
                 return SScalar("i64", "(long long)" + K.let("int", code), a.prov)
@@ -1697,6 +1773,19 @@ def merge_code(q, K):
         for j in range(len(t.fields)):
             L.append("                td.agg[%d] = c.%s_a%d;" % (j, t.name, j))
         L.append("                if (a->merge(a->merge_ctx, (unsigned long long)(uintptr_t)&td, 0, SDQLB200_MERGE_TABLE)) return sdqlhost::fail(SDQLB200_E_ARG, \"%s: merging hashed table %s across ranks failed\");" % (q.name, t.name))
+        nf64 = sum(1 for _, ct in t.fields if ct == "f64")
+        words = 1 + nf64 + 2 * (len(t.fields) - nf64)
+        L.append("            } else if (c.%s.cap <= sdqlrt::kFusedMergeMaxSlots) {  // small table: presence + all fields in ONE all-reduce" % t.name)
+        L.append("                sdqlrt::TblIO io; memset(&io, 0, sizeof io);")
+        L.append("                io.rep = c.%s.rep; io.cap = c.%s.cap; io.nf = %d; io.f64_mask = %du;" %
+                 (t.name, t.name, len(t.fields), sum(1 << j for j, (_, ct) in enumerate(t.fields) if ct == "f64")))
+        for j in range(len(t.fields)):
+            L.append("                io.agg[%d] = (sdqlrt::u64*)c.%s_a%d;" % (j, t.name, j))
+        L.append("                const int og = sdqlhost::grid_for(c.%s.cap, 8, sms);" % t.name)
+        L.append("                SDQL_LAUNCH(sdqlrt::k_merge_pack, og, sdqlrt::kBlock, 0, st, io, a->rank, mg_%s);" % t.name)
+        L.append("                if (a->merge(a->merge_ctx, %s, (unsigned long long)c.%s.cap * %dull, SDQLB200_SUM_F64)) return sdqlhost::fail(SDQLB200_E_ARG, \"merge callback failed\");" %
+                 (off % ("mg_%s" % t.name), t.name, words))
+        L.append("                SDQL_LAUNCH(sdqlrt::k_merge_unpack, og, sdqlrt::kBlock, 0, st, io, a->rank, mg_%s);" % t.name)
         L.append("            } else {")
         L.append("            const int og = sdqlhost::grid_for(c.%s.cap, 8, sms);" % t.name)
         L.append("            SDQL_LAUNCH(sdqlrt::k_owner_encode, og, sdqlrt::kBlock, 0, st, c.%s.rep, own_%s, c.%s.cap, a->rank);" % (t.name, t.name, t.name))
@@ -1741,6 +1830,8 @@ def render_query(q):
         for j, (_, ct) in enumerate(t.fields):
             L.append("    %s* %s_a%d;" % (CT[ct], t.name, j))
     for K in q.kernels:
+        if K.body2 is not None:
+            L.append("    unsigned %s_qo;  // per-warp queues of surviving row ids: offset in dynamic shared memory" % K.name)
         if K.byte_cols:
             L.append("    unsigned %s_bo;  // byte-row staging buffers: offset in dynamic shared memory" % K.name)
         if K.pipe_mode() == "tma":
@@ -1800,6 +1891,9 @@ def render_query(q):
         L.append("    }")
     for t in q.tables:
         L.append("    int* own_%s = a->merge ? ar.alloc<int>(c.%s.cap) : nullptr;" % (t.name, t.name))
+        nf64 = sum(1 for _, ct in t.fields if ct == "f64")
+        L.append("    double* mg_%s = (a->merge && c.%s.cap <= sdqlrt::kFusedMergeMaxSlots) ? ar.alloc<double>(c.%s.cap * %d) : nullptr;" %
+                 (t.name, t.name, t.name, 1 + nf64 + 2 * (len(t.fields) - nf64)))
     L.append("    const unsigned long long tail_off = ar.used;  // scalars, counters, partials: zeroed before every run")
     L.append("    c.sc = ar.alloc<double>(%d); c.cnt = ar.alloc<unsigned>(%d); c.tcount = ar.alloc<unsigned long long>(%d);" %
              (max(1, q.nsc), max(1, q.ncnt), max(1, q.ntcount)))
@@ -1826,9 +1920,13 @@ def render_query(q):
             fn = "(const void*)%s<2>" % K.name
         else:
             fn = "(const void*)%s" % K.name
+        if K.body2 is not None:
+            L.append("        c.%s_qo = (unsigned)((sm_%s + 15) & ~(size_t)15); sm_%s = c.%s_qo + (sdqlrt::kBlock / sdqlrt::kLanes) * sdqlrt::kQueueSlots * 4;" %
+                     (K.name, K.name, K.name, K.name))
         if K.byte_cols:
+            # 16 bytes of slack on both sides: the word-wise string search reads whole aligned words around a row
             L.append("        c.%s_bo = (unsigned)((sm_%s + 15) & ~(size_t)15); sm_%s = c.%s_bo + %du;" %
-                     (K.name, K.name, K.name, K.name, 1024 * sum(K.byte_cols.values())))
+                     (K.name, K.name, K.name, K.name, 32 + 1024 * sum(K.byte_cols.values())))
         if ring:
             widths = " + ".join({"i32": "4", "f64": "8", "code": "(size_t)a->cols[%d].width" % idx}[rep]
                                 for (col, rep), (arr, idx) in K.scan_cols.items())
@@ -1913,7 +2011,8 @@ def render_query(q):
             L.append("        if (!merged_) {")
             if K.byte_cols:
                 L.append("            sdqlhost_occupancy((const void*)%s<3>, sm_%s);  // raises the dynamic shared memory limit" % (K.name, K.name))
-            L.append("            SDQL_LAUNCH(%s<3>, g_%s, sdqlrt::kBlock, %s, st, c);" % (K.name, K.name, "sm_%s" % K.name if K.byte_cols else "0"))
+            L.append("            SDQL_LAUNCH(%s<3>, g_%s, sdqlrt::kBlock, %s, st, c);" %
+                     (K.name, K.name, "sm_%s" % K.name if (K.byte_cols or K.body2 is not None) else "0"))
             L.append("            SDQL_CUDA(cudaGetLastError());")
             L.append("            unsigned long long h_cnt = 0;")
             L.append("            SDQL_CUDA(cudaMemcpyAsync(&h_cnt, c.tcount + %d, 8, cudaMemcpyDeviceToHost, st));" % K.count_slot)
@@ -1922,7 +2021,8 @@ def render_query(q):
                 nf = len(t.fields)
                 L.append("            {")
                 L.append("                void* ag[%d] = {%s};" % (max(1, nf), ", ".join("c.%s_a%d" % (t.name, j) for j in range(nf)) or "nullptr"))
-                L.append("                sdqlhost::replan_table(&c.%s, (char*)a->workspace, &tr[%d], (long long)h_cnt, ag);" % (t.name, t.index))
+                L.append("                const bool rp_ = sdqlhost::replan_table(&c.%s, (char*)a->workspace, &tr[%d], (long long)h_cnt, ag);" % (t.name, t.index))
+                L.append("                if (sdqlhost::debug()) fprintf(stderr, \"[sdqlb200] %s: %%llu rows reach the build of %s -> %%s, %%lld slots%%s\\n\", h_cnt, c.%s.direct ? \"direct\" : \"hash\", (long long)c.%s.cap, rp_ ? \" (re-planned)\" : \"\");" % (K.name, t.name, t.name, t.name))
                 for j, (_, ct) in enumerate(t.fields):
                     L.append("                c.%s_a%d = (%s*)ag[%d];" % (t.name, j, CT[ct], j))
                 L.append("            }")
@@ -1942,6 +2042,9 @@ def render_query(q):
             L.append("    SDQL_LAUNCH(%s, g_%s, sdqlrt::kBlock, sm_%s, st, c);" % (K.name, K.name, K.name))
         L.append("    SDQL_CUDA(cudaGetLastError()); ++launches;")
         L += merge_code(q, K)
+        for t in bits_tabs:  # presence bits of the finished table (one pass over its slots)
+            L.append("    if (c.%s.bits) { SDQL_LAUNCH(sdqlrt::k_tbl_bits, sdqlhost::grid_for(c.%s.cap, 8, sms), sdqlrt::kBlock, 0, st, c.%s); SDQL_CUDA(cudaGetLastError()); }" %
+                     (t.name, t.name, t.name))
         L.append("    if (kt && launches < 24) SDQL_CUDA(cudaEventRecord(sdqlhost_kev(launches), st));")
     L.append("    SDQL_CUDA(cudaEventRecord(sdqlhost_ev(1), st));")
     L.append("    a->launches = launches;")

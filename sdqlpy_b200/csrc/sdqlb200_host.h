@@ -167,8 +167,12 @@ static inline unsigned long long count_min_bytes() {
 // ... and whose reservation is at least this many times the bytes the cardinality pass has to scan
 static inline unsigned long long count_min_ratio() {
     static long long v = -1;
-    if (v < 0) { const char* e = getenv("SDQLB200_COUNT_MIN_RATIO"); v = e ? atoll(e) : 2; if (v < 0) v = 0; }
+    if (v < 0) { const char* e = getenv("SDQLB200_COUNT_MIN_RATIO"); v = e ? atoll(e) : 4; if (v < 0) v = 0; }
     return (unsigned long long)v;
+}
+static inline bool debug() {
+    static const bool d = getenv("SDQLB200_DEBUG") && getenv("SDQLB200_DEBUG")[0] == '1';
+    return d;
 }
 
 // Column tile ring (generated rel-scan kernels, "tma" pipeline): pick the number of stages and the CTAs per SM the

@@ -42,6 +42,7 @@ constexpr int kLanes = 32;    // threads that share one byte-row staging buffer 
 constexpr int kLanes = 1;
 #endif
 constexpr int kStageRows = kLanes * kVec;  // rows one warp stages per iteration
+constexpr int kQueueSlots = kLanes * kVec + kLanes;  // hit compaction: row ids one warp can hold (leftover < kLanes + one iteration)
 constexpr u64 kEmpty = ~0ull;
 
 // ---------------------------------------------------------------------------------------------
@@ -132,6 +133,14 @@ SDQL_DEV void stage_rows(unsigned char* dst, const unsigned char* col, i64 row0,
 #endif
 }
 
+#ifndef SDQLB200_EMU
+SDQL_DEV unsigned warp_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+SDQL_DEV void warp_sync() { __syncwarp(); }
+#else
+SDQL_DEV unsigned warp_ballot(bool p) { return p ? 1u : 0u; }
+SDQL_DEV void warp_sync() {}
+#endif
+
 // dictionary-code columns are uint8 when the dictionary has <= 256 entries, int32 otherwise (uniform branch)
 SDQL_DEV void ld4_code(const void* p, i64 i0, int width, int (&v)[4]) {
     if (width == 1) ld4((const unsigned char*)p + i0, v);
@@ -161,13 +170,6 @@ SDQL_DEV bool tbl_maybe(const Tbl& t, u64 key) {
     const u64 b = t.bmod ? key % t.bmod : key;
     return (ld1(t.bits + (b >> 5)) >> (unsigned)(b & 31)) & 1u;
 }
-SDQL_DEV void tbl_mark(const Tbl& t, u64 key) {
-    if (!t.bits) return;
-    const u64 b = t.bmod ? key % t.bmod : key;
-    const unsigned m = 1u << (unsigned)(b & 31);
-    if (!(t.bits[b >> 5] & m)) atomicOr(t.bits + (b >> 5), m);
-}
-
 SDQL_DEV u64 hash64(u64 x) {  // splitmix64 finaliser
     x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
     return x;
@@ -192,7 +194,6 @@ SDQL_DEV int tbl_upsert(const Tbl& t, u64 key, int src, bool& is_new) {
         int old = t.rep[key];
         if (old < 0) old = atomicCAS(t.rep + key, -1, src);
         is_new = old < 0;
-        if (is_new) tbl_mark(t, key);
         return (int)key;
     }
     u64 m = (u64)t.cap - 1, h = hash64(key) & m;
@@ -201,7 +202,7 @@ SDQL_DEV int tbl_upsert(const Tbl& t, u64 key, int src, bool& is_new) {
         if (k == key) { is_new = false; return (int)h; }
         if (k == kEmpty) {
             u64 prev = atomicCAS(t.keys + h, kEmpty, key);
-            if (prev == kEmpty) { t.rep[h] = src; is_new = true; tbl_mark(t, key); return (int)h; }
+            if (prev == kEmpty) { t.rep[h] = src; is_new = true; return (int)h; }
             if (prev == key) { is_new = false; return (int)h; }
         }
         h = (h + 1) & m;
@@ -225,6 +226,46 @@ SDQL_DEV i64 unpack_part(u64 key, i64 mn, i64 rng, i64 mul) {
     return (i64)((key / (u64)mul) % (u64)rng) + mn;
 }
 SDQL_DEV u64 tbl_key(const Tbl& t, i64 slot) { return t.direct ? (u64)slot : ld1(t.keys + slot); }
+
+// presence filter of a finished table: one pass over its slots right after the build kernel (no per-insert atomics in
+// the build).  A warp examines 32 consecutive slots; when their bits fall into one word (direct tables: always, unless
+// the first-part modulus wraps inside the group) the warp issues a single atomicOr.
+__global__ void k_tbl_bits(Tbl t) {
+#ifndef SDQLB200_EMU
+    const int lane = threadIdx.x & 31;
+    const i64 nwarp = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 base = ((((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5); base < t.cap; base += nwarp << 5) {
+        const i64 i = base + lane;
+        bool occ = false;
+        u64 key = 0;
+        if (i < t.cap) {
+            if (t.direct) { occ = t.rep[i] != -1; key = (u64)i; }
+            else { key = t.keys[i]; occ = key != kEmpty; }
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, occ);
+        if (!any) continue;
+        const u64 b = occ ? (t.bmod ? key % t.bmod : key) : 0;
+        const unsigned long long word = b >> 5;
+        const unsigned m = occ ? 1u << (unsigned)(b & 31) : 0u;
+        const int leader = __ffs(any) - 1;
+        const unsigned long long w0 = __shfl_sync(0xffffffffu, word, leader);
+        if (__all_sync(0xffffffffu, !occ || word == w0)) {
+            const unsigned r = __reduce_or_sync(0xffffffffu, m);
+            if (lane == leader) atomicOr(t.bits + w0, r);
+        } else if (occ) {
+            atomicOr(t.bits + word, m);
+        }
+    }
+#else
+    for (i64 i = 0; i < t.cap; ++i) {
+        const bool occ = t.direct ? t.rep[i] != -1 : t.keys[i] != kEmpty;
+        if (!occ) continue;
+        const u64 key = t.direct ? (u64)i : t.keys[i];
+        const u64 b = t.bmod ? key % t.bmod : key;
+        t.bits[b >> 5] |= 1u << (unsigned)(b & 31);
+    }
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // atomics / reductions
@@ -335,6 +376,39 @@ struct TblIO {
     unsigned f64_mask;  // bit j: field j is fp64 (else int64)
     u64* agg[16];
 };
+// small direct-indexed tables (low-cardinality group-by: the common case) are merged with ONE all-reduce: presence,
+// fp64 fields and int64 fields travel together as fp64 words of one staging buffer [1 + nf64 + 2 * ni64][cap]:
+//   presence   2^rank if this rank has the key (sum = bit mask of the ranks that saw it; owner = lowest set bit)
+//   fp64 field the value itself (exactly the in-place all-reduce)
+//   int64      high and low 32-bit halves as two exact fp64 words (sums stay below 2^53); re-assembled modulo 2^64
+__global__ void k_merge_pack(TblIO t, int rank, double* mg) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < t.cap; i += (i64)gridDim.x * blockDim.x) {
+        mg[i] = t.rep[i] >= 0 ? (double)(1ull << rank) : 0.0;
+        i64 col = 1;
+        for (int j = 0; j < t.nf; ++j) {
+            const u64 v = t.agg[j][i];
+            if ((t.f64_mask >> j) & 1u) { mg[col * t.cap + i] = __longlong_as_double((i64)v); col += 1; }
+            else { mg[col * t.cap + i] = (double)(v >> 32); mg[(col + 1) * t.cap + i] = (double)(v & 0xffffffffull); col += 2; }
+        }
+    }
+}
+__global__ void k_merge_unpack(TblIO t, int rank, const double* mg) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < t.cap; i += (i64)gridDim.x * blockDim.x) {
+        const u64 mask = (u64)mg[i];
+        if (mask) {
+            int owner = 0;
+            while (!((mask >> owner) & 1ull)) ++owner;
+            if (owner != rank) t.rep[i] = -2;  // present, iterated (late-materialised) by its owner rank
+        }
+        i64 col = 1;
+        for (int j = 0; j < t.nf; ++j) {
+            if ((t.f64_mask >> j) & 1u) { t.agg[j][i] = (u64)__double_as_longlong(mg[col * t.cap + i]); col += 1; }
+            else { t.agg[j][i] = ((u64)mg[col * t.cap + i] << 32) + (u64)mg[(col + 1) * t.cap + i]; col += 2; }
+        }
+    }
+}
+constexpr i64 kFusedMergeMaxSlots = 65536;
+
 SDQL_DEV int shuffle_dest(u64 key, int world) { return (int)((hash64(key ^ 0x9e3779b97f4a7c15ull) >> 33) % (u64)world); }
 
 __global__ void k_tbl_count(TblIO t, int world, u64* counts) {
@@ -396,16 +470,58 @@ SDQL_DEV int str_len(const unsigned char* s, int w) {
     return n;
 }
 // first index of pat in s, -1 if absent (varchar.h:91-97 firstIndex -> wcsstr, which stops at the first NUL)
-// single pass: a match cannot start at or span a NUL (patterns contain none), so the scan simply stops at the first NUL
+// single pass: a match cannot start at or span a NUL (patterns contain none), so the scan simply stops at the first NUL.
+// Four characters are loaded per step, one step ahead of their use: the early-exit branches do not wait on a load each.
 SDQL_DEV int str_find(const unsigned char* s, int w, const char* pat, int plen) {
+    const int nst = w - plen + 1;  // start positions
+    if (nst <= 0) return -1;
     const unsigned char p0 = (unsigned char)pat[0];
-    for (int i = 0; i + plen <= w; ++i) {
-        const unsigned char ch = s[i];
-        if (ch == 0) return -1;
-        if (ch == p0) {
-            int j = 1;
-            while (j < plen && s[i + j] == (unsigned char)pat[j]) ++j;
-            if (j == plen) return i;
+    unsigned char c0 = s[0], c1 = 1 < w ? s[1] : 0, c2 = 2 < w ? s[2] : 0, c3 = 3 < w ? s[3] : 0;
+    for (int i = 0; i < nst; i += 4) {
+        const unsigned char d0 = i + 4 < w ? s[i + 4] : 0, d1 = i + 5 < w ? s[i + 5] : 0, d2 = i + 6 < w ? s[i + 6] : 0,
+                            d3 = i + 7 < w ? s[i + 7] : 0;
+        const unsigned char cc[4] = {c0, c1, c2, c3};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i + j >= nst || cc[j] == 0) return -1;
+            if (cc[j] == p0) {
+                int k = 1;
+                while (k < plen && s[i + j + k] == (unsigned char)pat[k]) ++k;
+                if (k == plen) return i + j;
+            }
+        }
+        c0 = d0; c1 = d1; c2 = d2; c3 = d3;
+    }
+    return -1;
+}
+// str_find for rows staged in shared memory (16 readable bytes on both sides of the buffers): the row is read as
+// aligned 32-bit words (re-aligned with a funnel shift), four characters per step; a word with neither a NUL nor the
+// pattern's first character is skipped with a handful of ALU instructions.  The next word is loaded before the current
+// one is examined, so the loop-carried branch does not wait on shared-memory latency.
+SDQL_DEV int str_find_w(const unsigned char* s, int w, const char* pat, int plen) {
+    const int last = w - plen;  // last possible start
+    if (last < 0) return -1;
+    const unsigned a = (unsigned)(size_t)s & 3u;
+    const unsigned* wp = (const unsigned*)(s - a);
+    const unsigned p0 = (unsigned char)pat[0];
+    const unsigned p0x4 = p0 * 0x01010101u;
+    unsigned lo = wp[0];
+    for (int i = 0; i <= last; i += 4) {
+        const unsigned hi = wp[(i >> 2) + 1];
+        const unsigned v = __funnelshift_r(lo, hi, a * 8u);  // characters s[i .. i+3]
+        lo = hi;
+        const unsigned x = v ^ p0x4;
+        const unsigned hit = ((v - 0x01010101u) & ~v & 0x80808080u) | ((x - 0x01010101u) & ~x & 0x80808080u);
+        if (!hit) continue;  // no NUL and no first character in these four
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned ch = (v >> (8 * j)) & 0xffu;
+            if (ch == 0u) return -1;
+            if (ch == p0 && i + j <= last) {
+                int k = 1;
+                while (k < plen && s[i + j + k] == (unsigned char)pat[k]) ++k;
+                if (k == plen) return i + j;
+            }
         }
     }
     return -1;
