@@ -49,10 +49,13 @@ PIPELINE = os.environ.get("SDQLB200_PIPELINE", "auto")  # auto | tma | reg | l2 
 PF_DIST = int(os.environ.get("SDQLB200_PF_DIST", "2"))
 RING_ROWS_PER_THREAD = int(os.environ.get("SDQLB200_RING_ROWS", "0"))  # 0 = per kernel (Kernel.ring_rows)
 RING_MAX_ROW_BYTES = 100     # wider scans cannot keep two stages in 227 KB of shared memory: they use LDGs
-BYTE_STAGING = os.environ.get("SDQLB200_BYTE_STAGING", "1") != "0"  # string columns of the scanned row go through shared memory
+# string columns of the scanned row staged through shared memory: measured on B200 (SF10) Q13 2.25 ms staged vs 1.80 ms
+# with plain (L1-cached) byte loads and the same look-ahead search, Q16/Q2 within noise -> opt-in
+BYTE_STAGING = os.environ.get("SDQLB200_BYTE_STAGING", "0") == "1"
 # measured on B200 (Q13, SF10): the word-wise search loses to the byte loop with look-ahead (every warp has some lane that
 # needs the per-character slow path), so it is opt-in
 STRFIND_W = os.environ.get("SDQLB200_STRFIND_W", "0") == "1"
+ROWS_AUTO = os.environ.get("SDQLB200_ROWS_AUTO", "1") != "0"  # narrow scans: 8 / 16 rows per thread per iteration
 COMPACT = os.environ.get("SDQLB200_COMPACT", "1") != "0"  # rows surviving a selective probe are queued and re-dealt to all lanes
 BITS_FILTER = os.environ.get("SDQLB200_BITS", "1") != "0"  # presence bitmaps in front of selective, probed tables
 COUNT_PASS = os.environ.get("SDQLB200_COUNT_PASS", "1") != "0"  # cardinality passes in front of selective table builds
@@ -400,6 +403,17 @@ class Kernel:
         self.depth -= 1
         self.emit("}")
 
+    def rows_per_thread(self):
+        """rows one thread handles per iteration (a multiple of 4: whole 128-bit loads).  Narrow scans (the filter phase
+        of a compacted kernel streams a key column or two) take 8 or 16 so that enough bytes are in flight per thread;
+        only where the per-row code is short (it is unrolled)."""
+        if self.src[0] != "rel" or self.byte_cols or not ROWS_AUTO:
+            return 4
+        if self.body2 is None and len(self.body) > 12:
+            return 4
+        b = sum({"i32": 4, "f64": 8, "code": 1}[rep] for (_, rep) in self.scan_cols)
+        return 16 if b <= 4 else 8 if b <= 12 else 4
+
     def scan_col(self, col, rep):
         k = (col, rep)
         if k not in self.scan_cols:
@@ -423,21 +437,25 @@ class Kernel:
             # software-pipelined streaming loop: the next group's column loads are issued before the current
             # group is processed, so every thread keeps two groups (2 x 4 rows x all columns) in flight
             ety = {"i32": "int", "f64": "double", "code": "int"}
+            R = self.rows_per_thread()
+            self.R = R
 
             def loads(prefix, gvar, ind):
                 o = []
                 o.append(ind + "{")
-                o.append(ind + "    const long long j0 = %s << 2;" % gvar)
-                o.append(ind + "    if (j0 + 4 <= n) {")
+                o.append(ind + "    const long long j0 = %s * %d;" % (gvar, R))
+                o.append(ind + "    if (j0 + %d <= n) {" % R)
                 for (col, rep), (arr, idx) in self.scan_cols.items():
                     dst = prefix + arr[2:]
                     cg = self.count_guard(col, rep)
-                    if rep == "code":
-                        o.append(ind + "        %ssdqlrt::ld4_code(c.in%d, j0, c.in%d_w, %s);" % (cg, idx, idx, dst))
-                    else:
-                        o.append(ind + "        %ssdqlrt::ld4(c.in%d + j0, %s);" % (cg, idx, dst))
+                    for v in range(0, R, 4):
+                        d4 = "reinterpret_cast<%s(&)[4]>(%s[%d])" % (ety[rep], dst, v)
+                        if rep == "code":
+                            o.append(ind + "        %ssdqlrt::ld4_code(c.in%d, j0 + %d, c.in%d_w, %s);" % (cg, idx, v, idx, d4))
+                        else:
+                            o.append(ind + "        %ssdqlrt::ld4(c.in%d + j0 + %d, %s);" % (cg, idx, v, d4))
                 o.append(ind + "    } else {")
-                o.append(ind + "        for (int u = 0; u < 4; ++u) {")
+                o.append(ind + "        for (int u = 0; u < %d; ++u) {" % R)
                 o.append(ind + "            const long long ii = (j0 + u < n) ? j0 + u : n - 1;")
                 for (col, rep), (arr, idx) in self.scan_cols.items():
                     dst = prefix + arr[2:]
@@ -452,13 +470,14 @@ class Kernel:
                 return o
 
             L.append("    const long long n = c.n_%s;" % self.src[1])
-            L.append("    const long long ngrp = (n + 3) >> 2;")
+            L.append("    const long long ngrp = (n + %d) / %d;" % (R - 1, R))
             L.append("    const long long gstride = (long long)gridDim.x * blockDim.x;")
             L.append("    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
             loop_cond = "g < ngrp"
             if self.body2 is not None:
                 loop_cond = "g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp"
-                L.append("    int* const wq = (int*)((unsigned char*)sm + c.%s_qo) + (threadIdx.x / sdqlrt::kLanes) * sdqlrt::kQueueSlots;" % self.name)
+                L.append("    int* const wq = (int*)((unsigned char*)sm + c.%s_qo) + (threadIdx.x / sdqlrt::kLanes) * (sdqlrt::kLanes * %d);" %
+                         (self.name, R + 1))
                 L.append("    const int lane_ = (int)(threadIdx.x & (sdqlrt::kLanes - 1));")
                 L.append("    int wcnt = 0;  // rows queued by this warp (the same value in every lane)")
             if self.byte_cols:
@@ -477,10 +496,11 @@ class Kernel:
                     return ["    while (%s) {" % cond]
                 # compaction: the drain below must also run once after the last scan iteration (one copy of the body)
                 return ["    for (;;) {", "    const bool more_ = %s;" % cond, "    if (more_) {"]
+
             pipe = self.pipe_mode() or "reg"
             if pipe == "reg":
                 for (col, rep), (arr, idx) in self.scan_cols.items():
-                    L.append("    %s %s[4], %s[4];" % (ety[rep], arr, "q_" + arr[2:]))
+                    L.append("    %s %s[%d], %s[%d];" % (ety[rep], arr, R, "q_" + arr[2:], R))
                 L.append("    if (g < ngrp)")
                 L += loads("r_", "g", "    ")
                 L += loop_head(loop_cond)
@@ -490,7 +510,7 @@ class Kernel:
                 L += stage
             else:  # "l2": single register buffer, the group PF_DIST iterations ahead is prefetched into L2
                 for (col, rep), (arr, idx) in self.scan_cols.items():
-                    L.append("    %s %s[4];" % (ety[rep], arr))
+                    L.append("    %s %s[%d];" % (ety[rep], arr, R))
                 L += loop_head(loop_cond)
                 L.append("        const long long gn = g + gstride;")
                 L += stage
@@ -498,14 +518,14 @@ class Kernel:
                 for (col, rep), (arr, idx) in self.scan_cols.items():
                     cg = self.count_guard(col, rep)
                     if rep == "code":
-                        L.append("            %ssdqlrt::prefetch_l2((const char*)c.in%d + (gp << 2) * c.in%d_w);" % (cg, idx, idx))
+                        L.append("            %ssdqlrt::prefetch_l2((const char*)c.in%d + (gp * %d) * c.in%d_w);" % (cg, idx, R, idx))
                     else:
-                        L.append("            %ssdqlrt::prefetch_l2(c.in%d + (gp << 2));" % (cg, idx))
+                        L.append("            %ssdqlrt::prefetch_l2(c.in%d + (gp * %d));" % (cg, idx, R))
                 L.append("        } }")
                 L += loads("r_", "g", "        ")
-            L.append("        const long long i0 = g << 2;")
+            L.append("        const long long i0 = g * %d;" % R)
             L.append("#pragma unroll")
-            L.append("        for (int u = 0; u < 4; ++u) {")
+            L.append("        for (int u = 0; u < %d; ++u) {" % R)
             L.append("            const long long i = i0 + u;")
             if self.body2 is not None:
                 L.append("            bool pass_ = false;")
@@ -522,7 +542,7 @@ class Kernel:
             L.append("        g = gn;")
             if self.scan_cols and pipe == "reg":
                 L.append("#pragma unroll")
-                L.append("        for (int u = 0; u < 4; ++u) {")
+                L.append("        for (int u = 0; u < %d; ++u) {" % R)
                 for (col, rep), (arr, idx) in self.scan_cols.items():
                     L.append("            %s[u] = %s[u];" % (arr, "q_" + arr[2:]))
                 L.append("        }")
@@ -1900,7 +1920,8 @@ def render_query(q):
     # launch plans: aggregation tier, shared memory (tier table + column tile ring), resident CTAs per SM, grid
     for K in q.kernels:
         if K.src[0] == "rel":
-            L.append("    const long long w_%s = (c.n_%s + 3) / 4;" % (K.name, K.src[1]))
+            R = getattr(K, "R", 4)
+            L.append("    const long long w_%s = (c.n_%s + %d) / %d;" % (K.name, K.src[1], R - 1, R))
         elif K.src[0] == "tbl":
             L.append("    const long long w_%s = c.%s.cap;" % (K.name, K.src[1].name))
         else:
@@ -1921,8 +1942,8 @@ def render_query(q):
         else:
             fn = "(const void*)%s" % K.name
         if K.body2 is not None:
-            L.append("        c.%s_qo = (unsigned)((sm_%s + 15) & ~(size_t)15); sm_%s = c.%s_qo + (sdqlrt::kBlock / sdqlrt::kLanes) * sdqlrt::kQueueSlots * 4;" %
-                     (K.name, K.name, K.name, K.name))
+            L.append("        c.%s_qo = (unsigned)((sm_%s + 15) & ~(size_t)15); sm_%s = c.%s_qo + (sdqlrt::kBlock / sdqlrt::kLanes) * (sdqlrt::kLanes * %d) * 4;" %
+                     (K.name, K.name, K.name, K.name, getattr(K, "R", 4) + 1))
         if K.byte_cols:
             # 16 bytes of slack on both sides: the word-wise string search reads whole aligned words around a row
             L.append("        c.%s_bo = (unsigned)((sm_%s + 15) & ~(size_t)15); sm_%s = c.%s_bo + %du;" %
@@ -2009,10 +2030,10 @@ def render_query(q):
             L.append("    if (cnt_%s) {" % K.name)
             L.append("        const bool merged_ = merged_%s;" % K.name)
             L.append("        if (!merged_) {")
-            if K.byte_cols:
+            uses_smem = bool(K.byte_cols or K.body2 is not None)
+            if uses_smem:  # same shared-memory layout as the real launch (queues / staging sit behind the tier table)
                 L.append("            sdqlhost_occupancy((const void*)%s<3>, sm_%s);  // raises the dynamic shared memory limit" % (K.name, K.name))
-            L.append("            SDQL_LAUNCH(%s<3>, g_%s, sdqlrt::kBlock, %s, st, c);" %
-                     (K.name, K.name, "sm_%s" % K.name if (K.byte_cols or K.body2 is not None) else "0"))
+            L.append("            SDQL_LAUNCH(%s<3>, g_%s, sdqlrt::kBlock, %s, st, c);" % (K.name, K.name, "sm_%s" % K.name if uses_smem else "0"))
             L.append("            SDQL_CUDA(cudaGetLastError());")
             L.append("            unsigned long long h_cnt = 0;")
             L.append("            SDQL_CUDA(cudaMemcpyAsync(&h_cnt, c.tcount + %d, 8, cudaMemcpyDeviceToHost, st));" % K.count_slot)

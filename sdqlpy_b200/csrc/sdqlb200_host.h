@@ -66,11 +66,11 @@ static inline unsigned long long up256(unsigned long long b) { return (b + 255) 
 // direct vs hash for `rows` distinct keys at most.  Direct when the dense array is not (much) bigger than what a hash
 // table for `rows` keys would need.  SDQLB200_FORCE_HASH=1 (debug knob): never direct -- exercises the hash build /
 // probe / merge paths at small scale.
-static inline void plan_table(long double dom, long long rows, int* direct, long long* cap) {
+static inline void plan_table(long double dom, long long rows, int* direct, long long* cap, long long sparse = 8) {
     static const bool force_hash = getenv("SDQLB200_FORCE_HASH") && getenv("SDQLB200_FORCE_HASH")[0] == '1';
     if (rows < 1) rows = 1;
     const long long domain = (long long)dom;
-    *direct = (!force_hash && dom <= (long double)(8 * rows + 65536) && domain < (1ll << 31)) ? 1 : 0;
+    *direct = (!force_hash && dom <= (long double)(sparse * rows + 65536) && domain < (1ll << 31)) ? 1 : 0;
     if (*direct) { *cap = domain; return; }
     const long long need = rows < domain ? rows : domain;
     long long c = 1024;
@@ -94,7 +94,9 @@ static inline void place_table(sdqlrt::Tbl* t, char* base, TblRegion* r, void** 
     for (int j = 0; j < r->nf; ++j) { aggs[j] = base ? (void*)(base + o) : nullptr; o += up256(n * 8); }
     t->bits = nullptr;
     t->bmod = r->bmod;
-    if (r->bdom && o - r->off >= bits_min_bytes()) {  // big table: presence bits in front of it
+    // presence bits in front of big tables (the bitmap stays cache resident) and of every hashed table (a bit test
+    // is far cheaper than hashing + probing, however small the table)
+    if (r->bdom && (!t->direct || o - r->off >= bits_min_bytes())) {
         t->bits = base ? (unsigned*)(base + o) : nullptr;
         o += bits_bytes(r->bdom);
     }
@@ -148,7 +150,9 @@ static inline bool size_table(sdqlrt::Tbl* t, int nparts, const long long* mn, c
 static inline bool replan_table(sdqlrt::Tbl* t, char* base, TblRegion* r, long long rows, void** aggs) {
     int direct;
     long long cap;
-    plan_table(r->dom, rows, &direct, &cap);
+    // with the true cardinality known, a dense array stays the better table down to one key per 64 slots: sorted
+    // builds and probes stream through it, while a hash table of millions of keys is built with random CAS traffic
+    plan_table(r->dom, rows, &direct, &cap, 64);
     if (table_bytes(direct, cap, r->nf) + bits_bytes(r->bdom) > r->len) return false;
     if (direct == t->direct && cap == t->cap) return false;
     t->direct = direct;

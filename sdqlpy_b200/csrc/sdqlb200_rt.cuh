@@ -234,6 +234,37 @@ __global__ void k_tbl_bits(Tbl t) {
 #ifndef SDQLB200_EMU
     const int lane = threadIdx.x & 31;
     const i64 nwarp = ((i64)gridDim.x * blockDim.x) >> 5;
+    if (t.direct && t.bmod == 0) {
+        // dense array, one bit per slot: every lane loads 4 x int4 (16 slots), a warp step covers 512 slots = 16 whole
+        // words of the bitmap, each assembled from the nibbles of 8 neighbouring lanes and written without atomics
+        // (the rep array is padded to 256 bytes: the last partial int4 is readable, its slots >= cap are masked)
+        const i64 nquad = (t.cap + 3) >> 2;
+        for (i64 q0 = (((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 128; q0 < nquad; q0 += nwarp * 128) {
+            int4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const i64 q = q0 + k * 32 + lane;
+                if (q < nquad) {
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(v[k].x), "=r"(v[k].y), "=r"(v[k].z), "=r"(v[k].w) : "l"(t.rep + 4 * q));
+                } else {
+                    v[k] = make_int4(-1, -1, -1, -1);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const i64 s0 = 4 * (q0 + k * 32 + lane);
+                unsigned nib = (v[k].x != -1 && s0 < t.cap ? 1u : 0u) | (v[k].y != -1 && s0 + 1 < t.cap ? 2u : 0u) |
+                               (v[k].z != -1 && s0 + 2 < t.cap ? 4u : 0u) | (v[k].w != -1 && s0 + 3 < t.cap ? 8u : 0u);
+                unsigned w = nib << (4 * (lane & 7));
+                w |= __shfl_xor_sync(0xffffffffu, w, 1);
+                w |= __shfl_xor_sync(0xffffffffu, w, 2);
+                w |= __shfl_xor_sync(0xffffffffu, w, 4);
+                if ((lane & 7) == 0 && w) t.bits[((q0 + k * 32) >> 3) + (lane >> 3)] = w;
+            }
+        }
+        return;
+    }
     for (i64 base = ((((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5); base < t.cap; base += nwarp << 5) {
         const i64 i = base + lane;
         bool occ = false;
