@@ -52,10 +52,12 @@ RING_MAX_ROW_BYTES = 100     # wider scans cannot keep two stages in 227 KB of s
 # string columns of the scanned row staged through shared memory: measured on B200 (SF10) Q13 2.25 ms staged vs 1.80 ms
 # with plain (L1-cached) byte loads and the same look-ahead search, Q16/Q2 within noise -> opt-in
 BYTE_STAGING = os.environ.get("SDQLB200_BYTE_STAGING", "0") == "1"
-# measured on B200 (Q13, SF10): the word-wise search loses to the byte loop with look-ahead (every warp has some lane that
-# needs the per-character slow path), so it is opt-in
-STRFIND_W = os.environ.get("SDQLB200_STRFIND_W", "0") == "1"
-ROWS_AUTO = os.environ.get("SDQLB200_ROWS_AUTO", "1") != "0"  # narrow scans: 8 / 16 rows per thread per iteration
+# firstIndex / contains: word-wise search with a two-character prefix filter (sdqlrt::str_find); 0 = byte loop
+STRFIND_W = os.environ.get("SDQLB200_STRFIND_W", "1") == "1"
+# narrow scans with 8 / 16 rows per thread per iteration (groups of 4 rows one CTA-width apart, so loads stay coalesced):
+# lost the B200 A/B at SF10 on 17 of 20 queries (profiles/r01_codegen_variants_ab2.json: Q16 0.47 vs 0.29 ms, Q5 0.67 vs
+# 0.56 ms), so 4 rows per thread stays the default
+ROWS_AUTO = os.environ.get("SDQLB200_ROWS_AUTO", "0") == "1"
 COMPACT = os.environ.get("SDQLB200_COMPACT", "1") != "0"  # rows surviving a selective probe are queued and re-dealt to all lanes
 BITS_FILTER = os.environ.get("SDQLB200_BITS", "1") != "0"  # presence bitmaps in front of selective, probed tables
 COUNT_PASS = os.environ.get("SDQLB200_COUNT_PASS", "1") != "0"  # cardinality passes in front of selective table builds
@@ -440,39 +442,42 @@ class Kernel:
             R = self.rows_per_thread()
             self.R = R
 
+            G = R // 4  # groups of 4 consecutive rows per thread per iteration, blockDim.x groups apart: every 128-bit
+            #             load instruction of a warp stays one contiguous run of bytes
+
             def loads(prefix, gvar, ind):
                 o = []
-                o.append(ind + "{")
-                o.append(ind + "    const long long j0 = %s * %d;" % (gvar, R))
-                o.append(ind + "    if (j0 + %d <= n) {" % R)
-                for (col, rep), (arr, idx) in self.scan_cols.items():
-                    dst = prefix + arr[2:]
-                    cg = self.count_guard(col, rep)
-                    for v in range(0, R, 4):
-                        d4 = "reinterpret_cast<%s(&)[4]>(%s[%d])" % (ety[rep], dst, v)
+                for k in range(G):
+                    o.append(ind + "{")
+                    o.append(ind + "    const long long j0 = (%s + %d * (long long)blockDim.x) << 2;" % (gvar, k))
+                    o.append(ind + "    if (j0 + 4 <= n) {")
+                    for (col, rep), (arr, idx) in self.scan_cols.items():
+                        dst = prefix + arr[2:]
+                        cg = self.count_guard(col, rep)
+                        d4 = "reinterpret_cast<%s(&)[4]>(%s[%d])" % (ety[rep], dst, 4 * k)
                         if rep == "code":
-                            o.append(ind + "        %ssdqlrt::ld4_code(c.in%d, j0 + %d, c.in%d_w, %s);" % (cg, idx, v, idx, d4))
+                            o.append(ind + "        %ssdqlrt::ld4_code(c.in%d, j0, c.in%d_w, %s);" % (cg, idx, idx, d4))
                         else:
-                            o.append(ind + "        %ssdqlrt::ld4(c.in%d + j0 + %d, %s);" % (cg, idx, v, d4))
-                o.append(ind + "    } else {")
-                o.append(ind + "        for (int u = 0; u < %d; ++u) {" % R)
-                o.append(ind + "            const long long ii = (j0 + u < n) ? j0 + u : n - 1;")
-                for (col, rep), (arr, idx) in self.scan_cols.items():
-                    dst = prefix + arr[2:]
-                    cg = self.count_guard(col, rep)
-                    if rep == "code":
-                        o.append(ind + "            %s%s[u] = sdqlrt::ld1_code(c.in%d, ii, c.in%d_w);" % (cg, dst, idx, idx))
-                    else:
-                        o.append(ind + "            %s%s[u] = sdqlrt::ld1(c.in%d + ii);" % (cg, dst, idx))
-                o.append(ind + "        }")
-                o.append(ind + "    }")
-                o.append(ind + "}")
+                            o.append(ind + "        %ssdqlrt::ld4(c.in%d + j0, %s);" % (cg, idx, d4))
+                    o.append(ind + "    } else {")
+                    o.append(ind + "        for (int u = 0; u < 4; ++u) {")
+                    o.append(ind + "            const long long ii = (j0 + u < n) ? j0 + u : n - 1;")
+                    for (col, rep), (arr, idx) in self.scan_cols.items():
+                        dst = prefix + arr[2:]
+                        cg = self.count_guard(col, rep)
+                        if rep == "code":
+                            o.append(ind + "            %s%s[%d + u] = sdqlrt::ld1_code(c.in%d, ii, c.in%d_w);" % (cg, dst, 4 * k, idx, idx))
+                        else:
+                            o.append(ind + "            %s%s[%d + u] = sdqlrt::ld1(c.in%d + ii);" % (cg, dst, 4 * k, idx))
+                    o.append(ind + "        }")
+                    o.append(ind + "    }")
+                    o.append(ind + "}")
                 return o
 
             L.append("    const long long n = c.n_%s;" % self.src[1])
-            L.append("    const long long ngrp = (n + %d) / %d;" % (R - 1, R))
-            L.append("    const long long gstride = (long long)gridDim.x * blockDim.x;")
-            L.append("    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
+            L.append("    const long long ngrp = (n + 3) >> 2;")
+            L.append("    const long long gstride = (long long)gridDim.x * blockDim.x * %d;" % G)
+            L.append("    long long g = (long long)blockIdx.x * blockDim.x * %d + threadIdx.x;" % G)
             loop_cond = "g < ngrp"
             if self.body2 is not None:
                 loop_cond = "g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp"
@@ -517,16 +522,16 @@ class Kernel:
                 L.append("        { const long long gp = g + %d * gstride; if (gp < ngrp) {" % PF_DIST)
                 for (col, rep), (arr, idx) in self.scan_cols.items():
                     cg = self.count_guard(col, rep)
-                    if rep == "code":
-                        L.append("            %ssdqlrt::prefetch_l2((const char*)c.in%d + (gp * %d) * c.in%d_w);" % (cg, idx, R, idx))
-                    else:
-                        L.append("            %ssdqlrt::prefetch_l2(c.in%d + (gp * %d));" % (cg, idx, R))
+                    for k in range(G):
+                        if rep == "code":
+                            L.append("            %ssdqlrt::prefetch_l2((const char*)c.in%d + ((gp + %d * (long long)blockDim.x) << 2) * c.in%d_w);" % (cg, idx, k, idx))
+                        else:
+                            L.append("            %ssdqlrt::prefetch_l2(c.in%d + ((gp + %d * (long long)blockDim.x) << 2));" % (cg, idx, k))
                 L.append("        } }")
                 L += loads("r_", "g", "        ")
-            L.append("        const long long i0 = g * %d;" % R)
             L.append("#pragma unroll")
             L.append("        for (int u = 0; u < %d; ++u) {" % R)
-            L.append("            const long long i = i0 + u;")
+            L.append("            const long long i = ((g + (u >> 2) * (long long)blockDim.x) << 2) + (u & 3);")
             if self.body2 is not None:
                 L.append("            bool pass_ = false;")
             L.append("            if (i < n) {")
@@ -1678,7 +1683,7 @@ class Query:
         if s == XF.StringContains:
             pat, subj = a, self.ev(e.inp3, env, K)
             ptr, w = self.str_ptr(K, subj)
-            fn = "str_find_w" if (ptr.startswith("(bs") and STRFIND_W) else "str_find"  # staged rows: word-wise search
+            fn = "str_find" if STRFIND_W else "str_find_bytes"
             return SScalar("bool", "(sdqlrt::%s(%s, %d, %s, %d) >= 0)" % (fn, ptr, w, cstr(pat.value), len(pat.value)), subj.prov)
         b = self.ev(e.inp2, env, K)
         if s in (XF.StartsWith, XF.EndsWith, XF.FirstIndex):
@@ -1686,8 +1691,8 @@ class Query:
                 raise CodegenError("pattern must be a string constant")
             ptr, w = self.str_ptr(K, a)
             fn = {XF.StartsWith: "str_starts", XF.EndsWith: "str_ends", XF.FirstIndex: "str_find"}[s]
-            if fn == "str_find" and ptr.startswith("(bs") and STRFIND_W:
-                fn = "str_find_w"  # staged rows: word-wise search in shared memory
+            if fn == "str_find" and not STRFIND_W:
+                fn = "str_find_bytes"
             code = "sdqlrt::%s(%s, %d, %s, %d)" % (fn, ptr, w, cstr(b.value), len(b.value))
             if s == XF.FirstIndex:
                 return SScalar("i64", "(long long)" + K.let("int", code), a.prov)

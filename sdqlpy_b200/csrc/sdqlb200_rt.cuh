@@ -503,7 +503,7 @@ SDQL_DEV int str_len(const unsigned char* s, int w) {
 // first index of pat in s, -1 if absent (varchar.h:91-97 firstIndex -> wcsstr, which stops at the first NUL)
 // single pass: a match cannot start at or span a NUL (patterns contain none), so the scan simply stops at the first NUL.
 // Four characters are loaded per step, one step ahead of their use: the early-exit branches do not wait on a load each.
-SDQL_DEV int str_find(const unsigned char* s, int w, const char* pat, int plen) {
+SDQL_DEV int str_find_bytes(const unsigned char* s, int w, const char* pat, int plen) {
     const int nst = w - plen + 1;  // start positions
     if (nst <= 0) return -1;
     const unsigned char p0 = (unsigned char)pat[0];
@@ -525,37 +525,47 @@ SDQL_DEV int str_find(const unsigned char* s, int w, const char* pat, int plen) 
     }
     return -1;
 }
-// str_find for rows staged in shared memory (16 readable bytes on both sides of the buffers): the row is read as
-// aligned 32-bit words (re-aligned with a funnel shift), four characters per step; a word with neither a NUL nor the
-// pattern's first character is skipped with a handful of ALU instructions.  The next word is loaded before the current
-// one is examined, so the loop-carried branch does not wait on shared-memory latency.
-SDQL_DEV int str_find_w(const unsigned char* s, int w, const char* pat, int plen) {
+
+// 0x80 in every byte of x that is zero (exact per byte)
+SDQL_DEV unsigned zero_bytes(unsigned x) { return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu); }
+
+// Word-wise search: the row is read as aligned 32-bit words (the row itself may start at any byte; the bytes in front of
+// it belong to the previous row of the column), four start positions per step.  A step is decided by three SWAR tests
+// -- a NUL among the four characters, the pattern's FIRST character at position j and its SECOND at j + 1 -- so the
+// per-character path runs only for a NUL (once per row) or a two-character prefix match (rare); a first-character-only
+// filter would send every warp down that path at nearly every step (some lane always sees the letter).  The next word
+// is loaded one step ahead of its use.  The last < 12 characters are searched by the byte loop, so no word beyond the
+// row's end is touched.
+SDQL_DEV int str_find(const unsigned char* s, int w, const char* pat, int plen) {
+    if (plen < 2 || w < 16) return str_find_bytes(s, w, pat, plen);
     const int last = w - plen;  // last possible start
     if (last < 0) return -1;
     const unsigned a = (unsigned)(size_t)s & 3u;
     const unsigned* wp = (const unsigned*)(s - a);
-    const unsigned p0 = (unsigned char)pat[0];
-    const unsigned p0x4 = p0 * 0x01010101u;
-    unsigned lo = wp[0];
-    for (int i = 0; i <= last; i += 4) {
-        const unsigned hi = wp[(i >> 2) + 1];
-        const unsigned v = __funnelshift_r(lo, hi, a * 8u);  // characters s[i .. i+3]
-        lo = hi;
-        const unsigned x = v ^ p0x4;
-        const unsigned hit = ((v - 0x01010101u) & ~v & 0x80808080u) | ((x - 0x01010101u) & ~x & 0x80808080u);
-        if (!hit) continue;  // no NUL and no first character in these four
+    const unsigned p0x4 = (unsigned char)pat[0] * 0x01010101u, p1x4 = (unsigned char)pat[1] * 0x01010101u;
+    unsigned w0 = wp[0], w1 = wp[1];
+    int i = 0;
+    for (; i + 12 <= w; i += 4) {  // reads up to the aligned word holding s[i + 11 - a]: inside the row
+        const unsigned w2 = wp[(i >> 2) + 2];
+        const unsigned v = __funnelshift_rc(w0, w1, a * 8u);        // characters i .. i+3
+        const unsigned v1 = __funnelshift_rc(w0, w1, a * 8u + 8u);  // characters i+1 .. i+4
+        w0 = w1;
+        w1 = w2;
+        const unsigned z = zero_bytes(v);
+        const unsigned m = zero_bytes(v ^ p0x4) & zero_bytes(v1 ^ p1x4);
+        if (!(z | m)) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const unsigned ch = (v >> (8 * j)) & 0xffu;
-            if (ch == 0u) return -1;
-            if (ch == p0 && i + j <= last) {
-                int k = 1;
+            if ((z >> (8 * j + 7)) & 1u) return -1;
+            if (((m >> (8 * j + 7)) & 1u) && i + j <= last) {
+                int k = 2;
                 while (k < plen && s[i + j + k] == (unsigned char)pat[k]) ++k;
                 if (k == plen) return i + j;
             }
         }
     }
-    return -1;
+    const int r = str_find_bytes(s + i, w - i, pat, plen);
+    return r < 0 ? -1 : r + i;
 }
 SDQL_DEV bool str_starts(const unsigned char* s, int w, const char* pat, int plen) {  // varchar.h:99-111
     if (plen > w) return false;

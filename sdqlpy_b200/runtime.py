@@ -83,6 +83,35 @@ class CudaBackend:
         from . import wire
         return wire.upload_decoded(packed, self)
 
+    def upload_overlapped(self, packed):
+        """asynchronous copy of a pinned packed image on a dedicated copy stream into the column's own device staging
+        buffer; the compute stream waits for exactly this copy.  -> device pointer of the staged image"""
+        t = self.torch
+        if getattr(self, "copy_stream", None) is None:
+            self.copy_stream = t.cuda.Stream(device=self.dev)
+        st = packed._stage
+        if st is None or st[0].device != self.dev:
+            st = [t.empty(packed._pin.numel(), dtype=t.uint8, device=self.dev), None]
+            packed._stage = st
+            self.copy_stream.wait_stream(t.cuda.current_stream())  # the allocation may reuse memory of earlier work
+        main = t.cuda.current_stream()
+        with t.cuda.stream(self.copy_stream):
+            if st[1] is not None:
+                self.copy_stream.wait_event(st[1])  # the previous expansion of this column has read the buffer
+            st[0].copy_(packed._pin.view(t.uint8).reshape(-1), non_blocking=True)
+            ev = t.cuda.Event()
+            ev.record(self.copy_stream)
+        main.wait_event(ev)
+        return st[0].data_ptr()
+
+    def decoded(self, packed):
+        """called after the expansion kernel of ``packed`` was enqueued on the compute stream"""
+        st = packed._stage
+        if st is not None:
+            ev = self.torch.cuda.Event()
+            ev.record(self.torch.cuda.current_stream())
+            st[1] = ev
+
     def pinned_like(self, arr):
         """copy of a numpy array in page-locked host memory (numpy view, backing tensor)."""
         t = self.torch.empty(arr.shape, dtype=self.torch.from_numpy(arr[:0]).dtype, pin_memory=True)

@@ -75,14 +75,14 @@ def bitunpack(stream, nbits, n):
 class Packed:
     """one packed column: ``codes`` (the image that crosses the link), ``table`` (dictionary, tiny) or ``scale``."""
     __slots__ = ("kind", "codes", "table", "scale", "rows", "rep", "min", "max", "nbits", "base", "dictionary",
-                 "_dev_table", "_pin")
+                 "_dev_table", "_pin", "_stage")
 
     def __init__(self, kind, codes, table=None, scale=0.0, rep="f64", mn=0, mx=0, nbits=0, base=0, rows=None,
                  dictionary=None):
         self.kind, self.codes, self.table, self.scale, self.rep = kind, codes, table, float(scale), rep
         self.rows = len(codes) if rows is None else int(rows)  # bit-packed kinds: codes is the byte stream
         self.min, self.max, self.nbits, self.base, self.dictionary = mn, mx, int(nbits), int(base), dictionary
-        self._dev_table, self._pin = None, None
+        self._dev_table, self._pin, self._stage = None, None, None
 
     @property
     def nbytes(self):
@@ -249,7 +249,12 @@ def upload_decoded(p, be):
     and expand it there."""
     L = lib()
     h2d = p.codes.nbytes
-    src_ptr, src_hold = be.upload(p.codes.view(np.uint8))
+    if p._pin is not None and hasattr(be, "upload_overlapped") and p.codes.nbytes >= (1 << 20):
+        # pinned image: the copy runs on the back end's copy stream into a staging buffer that belongs to this column,
+        # so the link keeps transferring the next column while this one is expanded on the compute stream
+        src_ptr = be.upload_overlapped(p)
+    else:
+        src_ptr, src_hold = be.upload(p.codes.view(np.uint8))
     tab_ptr = None
     if p.table is not None:
         if p._dev_table is None or p._dev_table[2] is not be:
@@ -264,5 +269,7 @@ def upload_decoded(p, be):
         rc = L.sdqlb200_wire_decode(p.kind, src_ptr, dst_ptr, p.rows, tab_ptr, p.scale, be.stream())
     if rc != 0:
         raise RuntimeError("sdqlb200_wire_decode failed (%d): %s" % (rc, L.sdqlb200_wire_last_error().decode()))
+    if hasattr(be, "decoded"):
+        be.decoded(p)
     # src_hold is dropped here: the caching allocator reuses it in stream order, after the decode kernel
     return dst_ptr, dst_hold, h2d

@@ -29,7 +29,7 @@ int main() {
         int plen = (int)strlen(p);
         if (rand() % 3 == 0 && len >= plen) memcpy(s + rand() % (len - plen + 1), p, plen);  // plant a match
         int r = naive_find(s, w, p, plen);
-        int a = sdqlrt::str_find(s, w, p, plen), b = sdqlrt::str_find_w(s, w, p, plen);
+        int a = sdqlrt::str_find(s, w, p, plen), b = sdqlrt::str_find_bytes(s, w, p, plen);
         ++n;
         if (a != r) { a = -99; }
         if (a != b || a != r) { if (bad < 5) printf("MISMATCH w=%d len=%d pat=%s ref=%d got=%d\n", w, len, p, a, b); ++bad; }

@@ -39,6 +39,7 @@ static inline void __threadfence() {}
 static inline void __syncwarp() {}
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) { s &= 31; return s ? (lo >> s) | (hi << (32 - s)) : lo; }
+static inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned s) { return s >= 32 ? hi : (s ? (lo >> s) | (hi << (32 - s)) : lo); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 static inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
