@@ -64,3 +64,16 @@ def _py(v):
 
 def run(mod, query, db):
     return normalise(getattr(mod, query + "_compiled")(db))
+
+
+def check(mod, query, db, got, compare, tries=3):
+    """compare ``got`` with the reference's result -> (difference or None, reference runs used).  The multi-threaded
+    reference fills its ``dense`` bool sets (Q4 / Q21 / Q22: ``vector<bool>``, sdql_ir_cpp_generator_par.py:205, 738-741)
+    from several threads without synchronisation, so neighbouring bits are occasionally lost and its own result changes
+    from run to run; a mismatch is therefore re-checked against fresh reference runs."""
+    d = None
+    for k in range(tries):
+        d = compare(got, run(mod, query, db))
+        if d is None:
+            return None, k + 1
+    return d, tries
