@@ -20,7 +20,7 @@ extern "C" {
 
 enum { SDQLB200_I32 = 0, SDQLB200_F64 = 1, SDQLB200_CODE = 2, SDQLB200_BYTES = 3 };
 enum { SDQLB200_OK = 0, SDQLB200_E_WORKSPACE = -1, SDQLB200_E_CUDA = -2, SDQLB200_E_ARG = -3, SDQLB200_E_NOQUERY = -4 };
-enum { SDQLB200_F_NOFETCH = 1, SDQLB200_F_KERNEL_TIMES = 2 };
+enum { SDQLB200_F_NOFETCH = 1, SDQLB200_F_KERNEL_TIMES = 2, SDQLB200_F_TRACE = 4 /* per-step wall-clock times on stderr */ };
 enum { SDQLB200_COL_PARTKEY = 1 };                       /* sdqlb200_col.flags: the relation is range partitioned on this column */
 enum { SDQLB200_SUM_F64 = 0, SDQLB200_SUM_I64 = 1, SDQLB200_MIN_I32 = 2, SDQLB200_MERGE_TABLE = 3 }; /* merge ops */
 /* multi-GPU: called (stream ordered) after a kernel over a partitioned relation for every partial buffer that has to
@@ -95,6 +95,13 @@ const char* sdqlb200_manifest(void);
 int sdqlb200_run(const char* query, sdqlb200_args* args);
 void sdqlb200_result_free(sdqlb200_result* r);
 const char* sdqlb200_last_error(void);
+
+/* Diagnostics (no reference counterpart): counters of the data-dependent memory operations executed since the previous
+ * call -- the inputs of the "bytes-moved" roofline of join-heavy queries.  out[0..7]: presence-bit tests, table probes,
+ * slots touched by probes, insert-or-find operations, slots they touched, global aggregate atomics, gather loads,
+ * (unused); out[8]: bytes of table arrays initialised (counted in every build).  Returns 1 when the module is a
+ * counting build (-DSDQLB200_STATS; such a build is never timed), 0 when out[0..7] are not collected, < 0 on error. */
+int sdqlb200_stats(uint64_t* out, int32_t n);
 
 /* building blocks of SDQLB200_MERGE_TABLE (all stream ordered; records are 2 + nfields 8-byte words:
  * key, owner rank, field values).  Records destined to rank d = hash(key) mod world.

@@ -79,8 +79,8 @@ def out_paths(script_path):
     return os.path.join(d, stem + "_compiled.cu"), os.path.join(d, stem + "_compiled.so")
 
 
-def nvcc(cu, so, verbose=False):
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-I", CSRC, "-I", INC, cu, "-o", so]
+def nvcc(cu, so, verbose=False, defines=()):
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-I", CSRC, "-I", INC, cu, "-o", so]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout[-4000:] + r.stderr[-8000:])
@@ -126,7 +126,7 @@ def compile_file(script_path, force=False, verbose=False):
               open(os.path.join(os.path.dirname(cu), "manifest.json"), "w"), indent=1)
     digest = hashlib.sha256(text.encode()).hexdigest()
     stamp = so + ".sha256"
-    deps = [os.path.join(CSRC, f) for f in ("sdqlb200_rt.cuh", "sdqlb200_host.h")] + [os.path.join(INC, "sdqlb200.h")]
+    deps = [os.path.join(CSRC, f) for f in ("sdqlb200_rt.cuh", "sdqlb200_textscan.cuh", "sdqlb200_host.h")] + [os.path.join(INC, "sdqlb200.h")]
     fresh = (os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == digest
              and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps))
     if fresh and not force:

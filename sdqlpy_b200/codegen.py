@@ -58,6 +58,10 @@ STRFIND_W = os.environ.get("SDQLB200_STRFIND_W", "1") == "1"
 # lost the B200 A/B at SF10 on 17 of 20 queries (profiles/r01_codegen_variants_ab2.json: Q16 0.47 vs 0.29 ms, Q5 0.67 vs
 # 0.56 ms), so 4 rows per thread stays the default
 ROWS_AUTO = os.environ.get("SDQLB200_ROWS_AUTO", "0") == "1"
+# firstIndex / contains on a scanned string column: the warp first streams its 128 rows' bytes with coalesced 128-bit loads
+# and marks the rows that contain the pattern's first four characters anywhere (sdqlrt::warp_text_scan); the exact
+# per-row search then runs for those candidate rows only
+TEXTSCAN = os.environ.get("SDQLB200_TEXTSCAN", "1") != "0"
 COMPACT = os.environ.get("SDQLB200_COMPACT", "1") != "0"  # rows surviving a selective probe are queued and re-dealt to all lanes
 BITS_FILTER = os.environ.get("SDQLB200_BITS", "1") != "0"  # presence bitmaps in front of selective, probed tables
 COUNT_PASS = os.environ.get("SDQLB200_COUNT_PASS", "1") != "0"  # cardinality passes in front of selective table builds
@@ -226,7 +230,8 @@ class TableDesc:
         if self.kind == "agg":
             vals = []
             for j, (fname, ct) in enumerate(self.fields):
-                vals.append((fname, SScalar(ct, "sdqlrt::ld1(c.%s_a%d + %s)" % (self.name, j, sl), prov=prov)))
+                ld = "ld1" if slot == "i" else "ldg1"  # sequential when the table itself is being scanned
+                vals.append((fname, SScalar(ct, "sdqlrt::%s(c.%s_a%d + %s)" % (ld, self.name, j, sl), prov=prov)))
             if self.inner is not None:
                 raise CodegenError("nested dictionary value used as a plain value")
             if self.scalar_value or self.count_only:
@@ -324,6 +329,7 @@ class Kernel:
         self.body2 = None         # hit compaction: the full body re-evaluated for a queued row id `iq` (all lanes busy)
         self.nprobe_sel = 0       # selective probes evaluated so far (lookups into tables built behind predicates)
         self.byte_cols = OrderedDict()  # input idx -> width: fixed-width string columns staged through shared memory
+        self.text_cols = OrderedDict()  # input idx -> [width, [patterns]]: scanned string columns with a warp text scan
         self.counted = False      # has a cardinality-pass variant (TIER == 3): predicates in front of a table build
         self.pred_cols = None     # scan columns the predicates read (the only ones the cardinality pass loads)
 
@@ -409,7 +415,7 @@ class Kernel:
         """rows one thread handles per iteration (a multiple of 4: whole 128-bit loads).  Narrow scans (the filter phase
         of a compacted kernel streams a key column or two) take 8 or 16 so that enough bytes are in flight per thread;
         only where the per-row code is short (it is unrolled)."""
-        if self.src[0] != "rel" or self.byte_cols or not ROWS_AUTO:
+        if self.src[0] != "rel" or self.byte_cols or self.text_cols or not ROWS_AUTO:
             return 4
         if self.body2 is None and len(self.body) > 12:
             return 4
@@ -430,7 +436,7 @@ class Kernel:
         tmpl = "template <int TIER>\n" if self.templated else ""
         L.append("%s__global__ void __launch_bounds__(sdqlrt::kBlock) %s(const __grid_constant__ %s_ctx c) {" %
                  (tmpl, self.name, q.name))
-        if self.tiered or self.pipe_mode() == "tma" or self.byte_cols or self.body2 is not None:
+        if self.tiered or self.pipe_mode() == "tma" or self.byte_cols or self.text_cols or self.body2 is not None:
             L.append("    SDQL_EXTERN_SMEM(sm);")
         L += ["    " + s for s in self.pre]
         if self.src[0] == "rel" and self.pipe_mode() == "tma":
@@ -495,6 +501,18 @@ class Kernel:
                     boff += 1024 * w
             stage = ["        sdqlrt::stage_rows(bs%d, c.in%d, (g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1))) << 2, n, %d);" % (idx, idx, w)
                      for idx, w in self.byte_cols.items()]
+            if self.text_cols:
+                # every lane of a warp runs the same number of iterations (the warp scans its rows' bytes cooperatively)
+                loop_cond = "g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp"
+                toff = 0
+                for idx, (w, pats) in self.text_cols.items():
+                    L.append("    unsigned* const tm%d = (unsigned*)((unsigned char*)sm + c.%s_to + %du) + (threadIdx.x / sdqlrt::kLanes) * (%d * sdqlrt::kTextWords);" %
+                             (idx, self.name, toff, len(pats)))
+                    L.append("    const unsigned tp%d[%d] = {%s};" % (idx, len(pats), ", ".join(
+                        "0x%08xu /* %s */" % (int.from_bytes(p_[:4].encode("latin1"), "little"), p_[:4].replace("*/", "")) for p_ in pats)))
+                    toff += 256 * 4 * len(pats)  # (kBlock / kLanes) warps x kTextWords words: at most 256 words per pattern
+                    stage.append("        sdqlrt::warp_text_scan<%d>(c.in%d, (g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1))) << 2, n, %d, tp%d, tm%d);" %
+                                 (len(pats), idx, w, idx, idx))
 
             def loop_head(cond):
                 if self.body2 is None:
@@ -1158,7 +1176,7 @@ class Query:
         if on_scan and not row.gather:
             code = K.scan_col(col, rep)
         else:
-            code = "sdqlrt::ld1(c.in%d + %s)" % (self.input(row.arg, col, rep), row.row)
+            code = "sdqlrt::ldg1(c.in%d + %s)" % (self.input(row.arg, col, rep), row.row)
         if rep == "i32":
             code = "(long long)" + code
         det = E
@@ -1174,18 +1192,36 @@ class Query:
             if s.scan:
                 return K.scan_col(s.col, "code")
             idx = self.input(s.arg, s.col, "code")
-            return "sdqlrt::ld1_code(c.in%d, %s, c.in%d_w)" % (idx, s.row, idx)
+            return "sdqlrt::ldg1_code(c.in%d, %s, c.in%d_w)" % (idx, s.row, idx)
         raise CodegenError("string of kind %s has no dictionary code" % s.kind)
 
     def str_ptr(self, K, s):
         if s.kind != "ref":
             raise CodegenError("pattern functions need a column string")
         idx = self.input(s.arg, s.col, "bytes")
+        if s.scan and K is not None and K.src == ("rel", s.arg):
+            if not hasattr(K, "str_scan"):
+                K.str_scan = OrderedDict()
+            K.str_scan[s.col] = s.width
         if s.scan and K is not None and K.src == ("rel", s.arg) and PIPELINE != "tma" and BYTE_STAGING:
             # the scanned row's bytes come from the warp's shared-memory staging buffer (Kernel.render / stage_rows)
             K.byte_cols[idx] = s.width
             return "(bs%d + (unsigned)(((threadIdx.x & (sdqlrt::kLanes - 1)) << 2) + u) * %du)" % (idx, s.width), s.width
         return "(c.in%d + (long long)(%s) * %d)" % (idx, s.row if not s.scan else "i", s.width), s.width
+
+    def text_candidate(self, K, s, pattern):
+        """firstIndex / contains of ``pattern`` in a string of the scanned row: register the pattern with the kernel's warp
+        text scan and return the C++ test "this row may contain it" (None: no scan for this string)."""
+        if not (TEXTSCAN and PIPELINE != "tma" and not BYTE_STAGING and isinstance(s, SStr) and s.kind == "ref" and s.scan
+                and K is not None and K.src == ("rel", s.arg) and len(pattern) >= 4 and "\0" not in pattern):
+            return None
+        idx = self.input(s.arg, s.col, "bytes")
+        w, pats = K.text_cols.setdefault(idx, [s.width, []])
+        if pattern not in pats:
+            if len(pats) >= 8:
+                return None
+            pats.append(pattern)
+        return "sdqlrt::text_cand(tm%d, %d, u & 3)" % (idx, pats.index(pattern))
 
     def part_code(self, K, x):
         """by-value key part -> (integer C++ expression, stats)."""
@@ -1459,7 +1495,7 @@ class Query:
             kval = SStr("codeval", arg=leaf.arg, col=leaf.col, code=cv)
         else:
             kval = SScalar("i64", cv, stats=inner_stats[0])
-        vals = [SScalar(ct, "sdqlrt::ld1(c.%s_a%d + %s)" % (t.name, j, sl)) for j, (_, ct) in enumerate(t.fields)]
+        vals = [SScalar(ct, "sdqlrt::ldg1(c.%s_a%d + %s)" % (t.name, j, sl)) for j, (_, ct) in enumerate(t.fields)]
         env2 = dict(env)
         env2[S.varExpr.name] = SPair(kval, vals[0] if (t.scalar_value or t.count_only) else
                                      SRec([(n, v) for (n, _), v in zip(t.fields, vals)]))
@@ -1675,7 +1711,7 @@ class Query:
             return SScalar("i64", "(%s / 10000)" % a.code, a.prov, E, st)
         if s == XF.DictSize:
             if isinstance(a, SLookup) and a.table.count_only:
-                return SScalar("i64", "(%s ? sdqlrt::ld1(c.%s_a0 + (%s < 0 ? 0 : %s)) : 0ll)" %
+                return SScalar("i64", "(%s ? sdqlrt::ldg1(c.%s_a0 + (%s < 0 ? 0 : %s)) : 0ll)" %
                                (a.found, a.table.name, a.slot, a.slot))
             if isinstance(a, SScalar):   # value of a distinct-count table (Q16)
                 return a
@@ -1684,7 +1720,8 @@ class Query:
             pat, subj = a, self.ev(e.inp3, env, K)
             ptr, w = self.str_ptr(K, subj)
             fn = "str_find" if STRFIND_W else "str_find_bytes"
-            return SScalar("bool", "(sdqlrt::%s(%s, %d, %s, %d) >= 0)" % (fn, ptr, w, cstr(pat.value), len(pat.value)), subj.prov)
+            cand = self.text_candidate(K, subj, pat.value)
+            return SScalar("bool", "(%ssdqlrt::%s(%s, %d, %s, %d) >= 0)" % (cand + " && " if cand else "", fn, ptr, w, cstr(pat.value), len(pat.value)), subj.prov)
         b = self.ev(e.inp2, env, K)
         if s in (XF.StartsWith, XF.EndsWith, XF.FirstIndex):
             if not (isinstance(b, SStr) and b.kind == "const"):
@@ -1694,6 +1731,9 @@ class Query:
             if fn == "str_find" and not STRFIND_W:
                 fn = "str_find_bytes"
             code = "sdqlrt::%s(%s, %d, %s, %d)" % (fn, ptr, w, cstr(b.value), len(b.value))
+            cand = self.text_candidate(K, a, b.value) if s == XF.FirstIndex else None
+            if cand:
+                code = "(%s ? %s : -1)" % (cand, code)
             if s == XF.FirstIndex:
                 return SScalar("i64", "(long long)" + K.let("int", code), a.prov)
             return SScalar("bool", code, a.prov)
@@ -1859,6 +1899,8 @@ def render_query(q):
             L.append("    unsigned %s_qo;  // per-warp queues of surviving row ids: offset in dynamic shared memory" % K.name)
         if K.byte_cols:
             L.append("    unsigned %s_bo;  // byte-row staging buffers: offset in dynamic shared memory" % K.name)
+        if K.text_cols:
+            L.append("    unsigned %s_to;  // text-scan candidate masks: offset in dynamic shared memory" % K.name)
         if K.pipe_mode() == "tma":
             L.append("    unsigned %s_ro; int %s_rs;  // column tile ring: byte offset in dynamic shared memory, stages" % (K.name, K.name))
     L.append("    double* sc; double* part; unsigned* cnt; unsigned long long* tcount;")
@@ -1953,6 +1995,9 @@ def render_query(q):
             # 16 bytes of slack on both sides: the word-wise string search reads whole aligned words around a row
             L.append("        c.%s_bo = (unsigned)((sm_%s + 15) & ~(size_t)15); sm_%s = c.%s_bo + %du;" %
                      (K.name, K.name, K.name, K.name, 32 + 1024 * sum(K.byte_cols.values())))
+        if K.text_cols:
+            L.append("        c.%s_to = (unsigned)((sm_%s + 15) & ~(size_t)15); sm_%s = c.%s_to + %du;" %
+                     (K.name, K.name, K.name, K.name, 1024 * sum(len(pats) for _, pats in K.text_cols.values())))
         if ring:
             widths = " + ".join({"i32": "4", "f64": "8", "code": "(size_t)a->cols[%d].width" % idx}[rep]
                                 for (col, rep), (arr, idx) in K.scan_cols.items())
@@ -2009,11 +2054,14 @@ def render_query(q):
                 scan = "(unsigned long long)c.%s.cap * 12ull" % K.src[1].name
             L.append("    const bool cnt_%s = (%s) >= sdqlhost::count_min_bytes() && (%s) >= sdqlhost::count_min_ratio() * (%s);" %
                      (K.name, tot, tot, scan))
+    L.append("    g_trace = (a->flags & SDQLB200_F_TRACE) != 0 || sdqlhost::debug();")
+    L.append("    sdqlhost_step(st, nullptr);")
     for t in q.tables:
         K = t.builder
         guard = "if (!cnt_%s) " % K.name if (K is not None and K.count_ok) else ""
         L.append("    %sSDQL_CUDA(sdqlhost_init_table(a->workspace, tr[%d], st));" % (guard, t.index))
     L.append("    SDQL_CUDA(cudaMemsetAsync((char*)a->workspace + tail_off, 0, zero_end - tail_off, st));")
+    L.append("    sdqlhost_step(st, \"%s:init\");" % n)
     L.append("    int launches = 0; const bool kt = (a->flags & SDQLB200_F_KERNEL_TIMES) != 0;")
     L.append("    if (kt) SDQL_CUDA(cudaEventRecord(sdqlhost_kev(0), st));")
     for K in q.kernels:
@@ -2035,7 +2083,7 @@ def render_query(q):
             L.append("    if (cnt_%s) {" % K.name)
             L.append("        const bool merged_ = merged_%s;" % K.name)
             L.append("        if (!merged_) {")
-            uses_smem = bool(K.byte_cols or K.body2 is not None)
+            uses_smem = bool(K.byte_cols or K.text_cols or K.body2 is not None)
             if uses_smem:  # same shared-memory layout as the real launch (queues / staging sit behind the tier table)
                 L.append("            sdqlhost_occupancy((const void*)%s<3>, sm_%s);  // raises the dynamic shared memory limit" % (K.name, K.name))
             L.append("            SDQL_LAUNCH(%s<3>, g_%s, sdqlrt::kBlock, %s, st, c);" % (K.name, K.name, "sm_%s" % K.name if uses_smem else "0"))
@@ -2043,6 +2091,7 @@ def render_query(q):
             L.append("            unsigned long long h_cnt = 0;")
             L.append("            SDQL_CUDA(cudaMemcpyAsync(&h_cnt, c.tcount + %d, 8, cudaMemcpyDeviceToHost, st));" % K.count_slot)
             L.append("            SDQL_CUDA(cudaStreamSynchronize(st));")
+            L.append("            sdqlhost_step(st, \"%s:count\");" % K.name)
             for t in owned[K]:
                 nf = len(t.fields)
                 L.append("            {")
@@ -2055,6 +2104,7 @@ def render_query(q):
             L.append("        }")
             for t in owned[K]:
                 L.append("        SDQL_CUDA(sdqlhost_init_table(a->workspace, tr[%d], st));" % t.index)
+            L.append("        sdqlhost_step(st, \"%s:table-init\");" % K.name)
             L.append("    }")
         if K.templated:
             if K.tiered:
@@ -2067,10 +2117,16 @@ def render_query(q):
         else:
             L.append("    SDQL_LAUNCH(%s, g_%s, sdqlrt::kBlock, sm_%s, st, c);" % (K.name, K.name, K.name))
         L.append("    SDQL_CUDA(cudaGetLastError()); ++launches;")
-        L += merge_code(q, K)
+        L.append("    sdqlhost_step(st, \"%s\");" % K.name)
+        mc = merge_code(q, K)
+        L += mc
+        if mc:
+            L.append("    sdqlhost_step(st, \"%s:merge\");" % K.name)
         for t in bits_tabs:  # presence bits of the finished table (one pass over its slots)
             L.append("    if (c.%s.bits) { SDQL_LAUNCH(sdqlrt::k_tbl_bits, sdqlhost::grid_for(c.%s.cap, 8, sms), sdqlrt::kBlock, 0, st, c.%s); SDQL_CUDA(cudaGetLastError()); }" %
                      (t.name, t.name, t.name))
+        if bits_tabs:
+            L.append("    sdqlhost_step(st, \"%s:bits\");" % K.name)
         L.append("    if (kt && launches < 24) SDQL_CUDA(cudaEventRecord(sdqlhost_kev(launches), st));")
     L.append("    SDQL_CUDA(cudaEventRecord(sdqlhost_ev(1), st));")
     L.append("    a->launches = launches;")
@@ -2092,7 +2148,9 @@ def manifest_of(q):
         "result_kind": q.result_kind,
         "result": [list(s) for s in (q.result_schema or [])],
         "kernels": [{"name": K.name, "source": list(K.src[:1]) + [K.src[1] if K.src[0] == "rel" else (K.src[1].name if K.src[0] == "tbl" else "")],
-                     "scan_cols": [[c, r] for (c, r) in K.scan_cols]} for K in q.kernels],
+                     "scan_cols": [[c, r] for (c, r) in K.scan_cols],
+                     # fixed-width string columns whose bytes the kernel reads for every scanned row: [column, width]
+                     "byte_cols": [[c, w] for (c, w) in getattr(K, "str_scan", {}).items()]} for K in q.kernels],
     }
 
 
@@ -2133,8 +2191,25 @@ static int sdqlhost_sms() {
 }
 #endif
 
+// SDQLB200_F_TRACE (or SDQLB200_DEBUG=1): wall-clock time of every step of the host driver on stderr (the stream is
+// drained after each step, so the figures are per step and the query as a whole runs slower than normal).
+// what == nullptr restarts the clock.
+static bool g_trace = false;
+static void sdqlhost_step(cudaStream_t st, const char* what) {
+    if (!g_trace) return;
+    static double last = 0;
+    cudaStreamSynchronize(st);
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    if (what) fprintf(stderr, "[sdqlb200] step %%-24s %%9.3f ms\n", what, now - last);
+    last = now;
+}
+
+static unsigned long long g_init_bytes = 0;  // bytes of table arrays initialised since the last sdqlb200_stats() call
 // fill a dictionary's key / representative arrays with 0xFF (free) and zero its aggregate arrays
 static cudaError_t sdqlhost_init_table(void* ws, const sdqlhost::TblRegion& r, cudaStream_t st) {
+    g_init_bytes += r.ff_len + r.z_len;
     cudaError_t e = cudaMemsetAsync((char*)ws + r.off, 0xFF, r.ff_len, st);
     if (e == cudaSuccess && r.z_len) e = cudaMemsetAsync((char*)ws + r.off + r.ff_len, 0, r.z_len, st);
     return e;
@@ -2196,6 +2271,29 @@ int sdqlb200_run(const char* query, sdqlb200_args* args) {
     for (int i = 0; i < sdqlb200_num_queries(); ++i)
         if (!strcmp(g_queries[i].name, query)) return g_queries[i].fn(args);
     return sdqlhost::fail(SDQLB200_E_NOQUERY, "no query named %%s in this module", query);
+}
+int sdqlb200_stats(uint64_t* out, int32_t n) {
+    if (!out || n < 0) return sdqlhost::fail(SDQLB200_E_ARG, "stats: bad arguments");
+    unsigned long long v[sdqlrt::kStCount + 1];
+    memset(v, 0, sizeof v);
+    int have = 0;
+#ifdef SDQLB200_STATS
+    have = 1;
+#ifndef SDQLB200_EMU
+    SDQL_CUDA(cudaDeviceSynchronize());
+    SDQL_CUDA(cudaMemcpyFromSymbol(v, sdqlrt::g_stats, sizeof(unsigned long long) * sdqlrt::kStCount));
+    unsigned long long z[sdqlrt::kStCount];
+    memset(z, 0, sizeof z);
+    SDQL_CUDA(cudaMemcpyToSymbol(sdqlrt::g_stats, z, sizeof z));
+#else
+    memcpy(v, sdqlrt::g_stats, sizeof(unsigned long long) * sdqlrt::kStCount);
+    memset(sdqlrt::g_stats, 0, sizeof(unsigned long long) * sdqlrt::kStCount);
+#endif
+#endif
+    v[sdqlrt::kStCount] = g_init_bytes;
+    g_init_bytes = 0;
+    for (int i = 0; i < n && i <= sdqlrt::kStCount; ++i) out[i] = v[i];
+    return have;
 }
 void sdqlb200_result_free(sdqlb200_result* r) {
     if (!r) return;

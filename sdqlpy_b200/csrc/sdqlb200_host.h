@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 
 #include "sdqlb200.h"
 #include "sdqlb200_rt.cuh"

@@ -46,6 +46,36 @@ constexpr int kQueueSlots = kLanes * kVec + kLanes;  // hit compaction: row ids 
 constexpr u64 kEmpty = ~0ull;
 
 // ---------------------------------------------------------------------------------------------
+// SDQLB200_STATS (diagnostic builds only, never timed): counts of the data-dependent memory operations of a query --
+// the inputs of the "bytes-moved" roofline of join-heavy queries (scan bytes + tables written + 32 B per
+// random access).  Read and reset through sdqlb200_stats().  A regular build compiles every stat() call to nothing.
+// ---------------------------------------------------------------------------------------------
+enum {
+    kStBitTests = 0,    // presence-bit tests (one 4-byte load each; the bitmap is L2 resident)
+    kStFinds = 1,       // probes that went past the presence bits into the table
+    kStFindSlots = 2,   // table slots those probes touched (1 for a direct table, the probe-chain length for a hashed one)
+    kStUpserts = 3,     // insert-or-find operations of table builds / group-bys
+    kStUpsertSlots = 4, // table slots they touched
+    kStAtomics = 5,     // global red.add on aggregate arrays
+    kStGathers = 6,     // data-dependent loads of column values / representative rows (late materialisation)
+    kStCount = 8
+};
+#ifdef SDQLB200_STATS
+#ifndef SDQLB200_EMU
+__device__ unsigned long long g_stats[kStCount];
+SDQL_DEV void stat(int k, unsigned long long n = 1) {
+    const unsigned m = __activemask();  // one atomic per converged group of lanes
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&g_stats[k], n * (unsigned long long)__popc(m));
+}
+#else
+static unsigned long long g_stats[kStCount];
+SDQL_DEV void stat(int k, unsigned long long n = 1) { g_stats[k] += n; }
+#endif
+#else
+SDQL_DEV void stat(int, unsigned long long = 1) {}
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // streaming loads
 // ---------------------------------------------------------------------------------------------
 #ifndef SDQLB200_EMU
@@ -134,6 +164,19 @@ SDQL_DEV void stage_rows(unsigned char* dst, const unsigned char* col, i64 row0,
 }
 
 #ifndef SDQLB200_EMU
+// primitives of the warp text scan (sdqlb200_textscan.cuh)
+SDQL_DEV int tx_lane() { return (int)(threadIdx.x & 31u); }
+SDQL_DEV void tx_syncwarp() { __syncwarp(); }
+SDQL_DEV unsigned tx_shfl_down(unsigned v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+SDQL_DEV void tx_atomic_or(unsigned* p, unsigned v) { atomicOr(p, v); }
+SDQL_DEV void tx_ldnc16(const unsigned char* p, unsigned (&w)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p));
+}
+#endif
+#include "sdqlb200_textscan.cuh"
+
+#ifndef SDQLB200_EMU
 SDQL_DEV unsigned warp_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 SDQL_DEV void warp_sync() { __syncwarp(); }
 #else
@@ -149,6 +192,9 @@ SDQL_DEV void ld4_code(const void* p, i64 i0, int width, int (&v)[4]) {
 SDQL_DEV int ld1_code(const void* p, i64 i, int width) {
     return width == 1 ? (int)ld1((const unsigned char*)p + i) : ld1((const int*)p + i);
 }
+// data-dependent (gather) loads of a column value at a row found through a table: late materialisation
+template <class T> SDQL_DEV T ldg1(const T* p) { stat(kStGathers); return ld1(p); }
+SDQL_DEV int ldg1_code(const void* p, i64 i, int width) { stat(kStGathers); return ld1_code(p, i, width); }
 
 // ---------------------------------------------------------------------------------------------
 // device dictionary
@@ -167,6 +213,7 @@ struct Tbl {
 
 SDQL_DEV bool tbl_maybe(const Tbl& t, u64 key) {
     if (!t.bits) return true;
+    stat(kStBitTests);
     const u64 b = t.bmod ? key % t.bmod : key;
     return (ld1(t.bits + (b >> 5)) >> (unsigned)(b & 31)) & 1u;
 }
@@ -178,9 +225,11 @@ SDQL_DEV u64 hash64(u64 x) {  // splitmix64 finaliser
 // -> slot or -1.  `ok` = every key part was inside the table's packing range.
 SDQL_DEV int tbl_find(const Tbl& t, u64 key, bool ok) {
     if (!ok || !tbl_maybe(t, key)) return -1;
-    if (t.direct) return ld1(t.rep + key) != -1 ? (int)key : -1;  // -2 = present, owned by another rank
+    stat(kStFinds);
+    if (t.direct) { stat(kStFindSlots); return ld1(t.rep + key) != -1 ? (int)key : -1; }  // -2 = present, owned by another rank
     u64 m = (u64)t.cap - 1, h = hash64(key) & m;
     for (;;) {
+        stat(kStFindSlots);
         u64 k = ld1(t.keys + h);
         if (k == key) return (int)h;
         if (k == kEmpty) return -1;
@@ -190,7 +239,9 @@ SDQL_DEV int tbl_find(const Tbl& t, u64 key, bool ok) {
 
 // insert-or-find; `src` becomes the slot's representative if the slot is new.  -> slot
 SDQL_DEV int tbl_upsert(const Tbl& t, u64 key, int src, bool& is_new) {
+    stat(kStUpserts);
     if (t.direct) {
+        stat(kStUpsertSlots);
         int old = t.rep[key];
         if (old < 0) old = atomicCAS(t.rep + key, -1, src);
         is_new = old < 0;
@@ -198,6 +249,7 @@ SDQL_DEV int tbl_upsert(const Tbl& t, u64 key, int src, bool& is_new) {
     }
     u64 m = (u64)t.cap - 1, h = hash64(key) & m;
     for (;;) {
+        stat(kStUpsertSlots);
         u64 k = t.keys[h];
         if (k == key) { is_new = false; return (int)h; }
         if (k == kEmpty) {
@@ -210,6 +262,7 @@ SDQL_DEV int tbl_upsert(const Tbl& t, u64 key, int src, bool& is_new) {
 }
 
 SDQL_DEV int rep_of(const Tbl& t, int slot) {  // safe for slot == -1 (returns a valid index >= 0)
+    if (slot >= 0) stat(kStGathers);
     int r = ld1(t.rep + (slot < 0 ? 0 : slot));
     return r < 0 ? 0 : r;
 }
@@ -301,8 +354,8 @@ __global__ void k_tbl_bits(Tbl t) {
 // ---------------------------------------------------------------------------------------------
 // atomics / reductions
 // ---------------------------------------------------------------------------------------------
-SDQL_DEV void red_add(double* p, double v) { atomicAdd(p, v); }
-SDQL_DEV void red_add(i64* p, i64 v) { atomicAdd((u64*)p, (u64)v); }
+SDQL_DEV void red_add(double* p, double v) { stat(kStAtomics); atomicAdd(p, v); }
+SDQL_DEV void red_add(i64* p, i64 v) { stat(kStAtomics); atomicAdd((u64*)p, (u64)v); }
 
 #ifndef SDQLB200_EMU
 template <class T> SDQL_DEV T warp_sum(T v) {

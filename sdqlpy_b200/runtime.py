@@ -22,6 +22,7 @@ KIND_ID = {"i32": 0, "f64": 1, "code": 2, "bytes": 3}
 E_WORKSPACE = -1
 F_NOFETCH = 1
 F_KERNEL_TIMES = 2
+F_TRACE = 4
 
 
 class Col(ctypes.Structure):
@@ -442,9 +443,9 @@ class CompiledModule:
         a.consts, a.nconsts = karr, len(consts)
         return a, (cols, carr, narr, karr)
 
-    def execute(self, name, a, fetch=True, kernel_times=False):
+    def execute(self, name, a, fetch=True, kernel_times=False, trace=False):
         be = backend()
-        a.flags = (0 if fetch else F_NOFETCH) | (F_KERNEL_TIMES if kernel_times else 0)
+        a.flags = (0 if fetch else F_NOFETCH) | (F_KERNEL_TIMES if kernel_times else 0) | (F_TRACE if trace else 0)
         a.stream = be.stream()
         a.workspace, a.workspace_bytes = (self.ws[0] if self.ws else None), self.ws_bytes
         if DIST is not None and DIST.world > 1:
@@ -464,6 +465,19 @@ class CompiledModule:
             extra = " [%r]" % (self.merge_error,) if self.merge_error is not None else ""
             raise RuntimeError("sdqlb200_run(%s) failed (%d): %s%s" % (name, rc, self.lib.sdqlb200_last_error().decode(), extra))
         return a
+
+    STAT_NAMES = ("bit_tests", "finds", "find_slots", "upserts", "upsert_slots", "atomics", "gathers", "_", "init_bytes")
+
+    def stats(self):
+        """counters since the previous call (sdqlb200_stats): -> (dict, counting_build).  Only a module built with
+        -DSDQLB200_STATS collects the device-side counters; ``init_bytes`` is available in every build."""
+        if not hasattr(self.lib, "sdqlb200_stats"):
+            return {}, False
+        out = (ctypes.c_uint64 * 9)()
+        rc = self.lib.sdqlb200_stats(out, 9)
+        if rc < 0:
+            raise RuntimeError("sdqlb200_stats failed (%d): %s" % (rc, self.lib.sdqlb200_last_error().decode()))
+        return {n: int(out[i]) for i, n in enumerate(self.STAT_NAMES) if n != "_"}, rc == 1
 
     def _merge(self, ctx, off, count, op):
         """sdqlb200_merge_fn: all-reduce `count` elements at workspace + off in place (NCCL on GPUs, gloo in tests)."""

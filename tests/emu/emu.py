@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 
 
-def build_emu(cu_path, so_path, opt="-O1"):
-    cmd = ["g++", "-x", "c++", "-std=c++17", opt, "-w", "-fPIC", "-shared", "-DSDQLB200_EMU", "-I", HERE,
+def build_emu(cu_path, so_path, opt="-O1", defines=()):
+    cmd = ["g++", "-x", "c++", "-std=c++17", opt, "-w", "-fPIC", "-shared", "-DSDQLB200_EMU"] + ["-D" + d for d in defines] + ["-I", HERE,
            "-I", os.path.join(ROOT, "sdqlpy_b200", "csrc"), "-I", os.path.join(ROOT, "include"), cu_path, "-o", so_path]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

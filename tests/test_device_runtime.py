@@ -15,3 +15,16 @@ def test_wordwise_string_search_matches_bytewise(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
     assert "0 mismatches" in r.stdout
+
+
+def test_warp_text_scan_32_lane_path(tmp_path):
+    """the 32-lane code path of sdqlrt::warp_text_scan (candidate rows for firstIndex / contains) run on the CPU, one
+    std::thread per lane: masks equal the scalar definition bit for bit, no matching row is missed, no byte behind the
+    column is read (guard page)."""
+    exe = os.path.join(tmp_path, "check_textscan")
+    src = os.path.join(ROOT, "tests", "emu", "check_textscan.cpp")
+    subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-w", "-I", os.path.join(ROOT, "sdqlpy_b200", "csrc"), src, "-o", exe],
+                   check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "0 mismatches" in r.stdout
