@@ -115,6 +115,18 @@ def compile_tpchgen(force=False):
     return nvcc(src, so)
 
 
+def compile_tbl(force=False):
+    """csrc/sdqlb200_tbl.cu -> sdqlpy_b200/_build/libsdqlb200_tbl.so (device-side .tbl reader, sm_100a)."""
+    src = os.path.join(CSRC, "sdqlb200_tbl.cu")
+    out_dir = os.path.join(PKG, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libsdqlb200_tbl.so")
+    deps = [src, os.path.join(INC, "sdqlb200_tbl.h"), os.path.join(INC, "sdqlb200.h")]
+    if not force and os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps):
+        return so
+    return nvcc(src, so)
+
+
 def compile_file(script_path, force=False, verbose=False):
     """generate + build the module of one query script; returns the .so path."""
     cu, so = out_paths(script_path)

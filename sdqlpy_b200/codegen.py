@@ -62,6 +62,11 @@ ROWS_AUTO = os.environ.get("SDQLB200_ROWS_AUTO", "0") == "1"
 # and marks the rows that contain the pattern's first four characters anywhere (sdqlrt::warp_text_scan); the exact
 # per-row search then runs for those candidate rows only
 TEXTSCAN = os.environ.get("SDQLB200_TEXTSCAN", "1") != "0"
+# Every scan-loop iteration ends with a full-warp sync (all lanes of a warp run the same number of iterations).  Lanes that
+# take a data-dependent slow path (an insertion with its probe loop, a hit behind a probe) otherwise do not rejoin their
+# warp: ncu showed q12_k0's main loop executing with 13 of 32 lanes active and 2.5x the warp-level instructions of the
+# cardinality pass over the same rows (profiles/r01_q12_k0_main_*.txt; SF100: 15.0 ms vs 1.3 ms).
+RECONVERGE = os.environ.get("SDQLB200_RECONVERGE", "1") != "0"
 COMPACT = os.environ.get("SDQLB200_COMPACT", "1") != "0"  # rows surviving a selective probe are queued and re-dealt to all lanes
 BITS_FILTER = os.environ.get("SDQLB200_BITS", "1") != "0"  # presence bitmaps in front of selective, probed tables
 COUNT_PASS = os.environ.get("SDQLB200_COUNT_PASS", "1") != "0"  # cardinality passes in front of selective table builds
@@ -485,6 +490,8 @@ class Kernel:
             L.append("    const long long gstride = (long long)gridDim.x * blockDim.x * %d;" % G)
             L.append("    long long g = (long long)blockIdx.x * blockDim.x * %d + threadIdx.x;" % G)
             loop_cond = "g < ngrp"
+            if RECONVERGE:
+                loop_cond = "g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp"
             if self.body2 is not None:
                 loop_cond = "g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp"
                 L.append("    int* const wq = (int*)((unsigned char*)sm + c.%s_qo) + (threadIdx.x / sdqlrt::kLanes) * (sdqlrt::kLanes * %d);" %
@@ -562,6 +569,8 @@ class Kernel:
                 L.append("                wcnt += __popc(m_);")
                 L.append("            }")
             L.append("        }")
+            if RECONVERGE:
+                L.append("        sdqlrt::warp_sync();  // lanes that took a slow path rejoin the warp here")
             L.append("        g = gn;")
             if self.scan_cols and pipe == "reg":
                 L.append("#pragma unroll")
@@ -1547,7 +1556,11 @@ class Query:
         if t.inner is not None:
             # `d[k] != None` on a dictionary-valued entry: subsumed by iterating the inner dictionary, which
             # yields nothing when no (k, *) entry exists (the only use in the workload is joinProbe, Q12)
-            lk.found = "true"
+            # With a presence filter in front of the table the test is "some (k, *) may exist": it gates the whole inner
+            # iteration (and is what the filter phase of a compacted kernel queues rows by); only its positive form is sound
+            lk.found = "(%s_outer_ok && sdqlrt::tbl_maybe_outer(c.%s, %s_outer, c.%s_rng[%d], c.%s_mul[%d]))" % (
+                sl, t.name, sl, t.name, t.inner[0], t.name, t.inner[0])
+            lk.found_is_filter = True
         return lk
 
     # -- expressions ---------------------------------------------------------------------------
@@ -1669,6 +1682,8 @@ class Query:
                 raise CodegenError("comparison with None needs a dictionary lookup")
             if lk.found is None:
                 raise CodegenError("None test on a nested dictionary lookup")
+            if op != CS.NE and getattr(lk, "found_is_filter", False):
+                raise CodegenError("== None on a dictionary-valued lookup is not supported")
             return SScalar("bool", lk.found if op == CS.NE else "(!%s)" % lk.found)
         a = a.value() if isinstance(a, SLookup) else a
         b = b.value() if isinstance(b, SLookup) else b

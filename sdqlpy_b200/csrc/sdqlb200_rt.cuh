@@ -217,6 +217,14 @@ SDQL_DEV bool tbl_maybe(const Tbl& t, u64 key) {
     const u64 b = t.bmod ? key % t.bmod : key;
     return (ld1(t.bits + (b >> 5)) >> (unsigned)(b & 31)) & 1u;
 }
+// dictionary-valued entry d[k] of a table keyed by (k, x): may any (k, x) be present?  outer = packed k, x in [0, rng)
+SDQL_DEV bool tbl_maybe_outer(const Tbl& t, u64 outer, i64 rng, i64 mul) {
+    if (!t.bits) return true;
+    if (t.bmod) return tbl_maybe(t, outer);
+    for (i64 x = 0; x < rng; ++x)
+        if (tbl_maybe(t, outer + (u64)x * (u64)mul)) return true;
+    return false;
+}
 SDQL_DEV u64 hash64(u64 x) {  // splitmix64 finaliser
     x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
     return x;

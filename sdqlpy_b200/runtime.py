@@ -124,6 +124,10 @@ class CudaBackend:
         d = self.torch.empty(max(int(nbytes), 256), dtype=self.torch.uint8, device=self.dev)
         return d.data_ptr(), d
 
+    def to_host(self, holder, nbytes):
+        """first ``nbytes`` bytes of a device buffer (the holder returned by alloc / upload) as a uint8 numpy array"""
+        return holder.view(self.torch.uint8).reshape(-1)[:int(nbytes)].cpu().numpy()
+
     def stream(self):
         return self.torch.cuda.current_stream().cuda_stream
 

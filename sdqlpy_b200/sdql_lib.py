@@ -226,6 +226,31 @@ def read_csv(file_path, header_type_dict, dataset_name, delimiter="|"):
     return sr_dict({"headers": heads, "data": data}, None, True)
 
 
+def read_tbl(file_path, header_type_dict, dataset_name, delimiter="|", columns=None):
+    """``read_csv`` with the parsing done on the GPU (sdqlpy_b200/tbl.py, csrc/sdqlb200_tbl.cu): same arguments, same
+    columnar ``sr_dict`` out, but the columns are compact (int32 / fp64 / fixed-width bytes) ``Column`` objects whose
+    device copies already sit in the column store.  ``columns``: optional subset of column names to parse (the others
+    stay ``None``; the first column is always parsed, it carries the row count)."""
+    from . import tbl
+    rec_type = list(header_type_dict.keys())[0].getContainer()
+    heads, types = list(rec_type.keys()), list(rec_type.values())
+    schema = []
+    for h, t in zip(heads, types):
+        if isinstance(t, string):
+            schema.append((h, ("str", t.max_size)))
+        elif t is date:
+            schema.append((h, "date"))
+        elif t is float:
+            schema.append((h, "float"))
+        elif t in (int, bool):
+            schema.append((h, "int"))
+        else:
+            raise ValueError("column %s: unsupported type %r" % (h, t))
+    want = None if columns is None else set(columns) | {heads[0]}
+    cols = tbl.parse_file(file_path, schema, want, delimiter)
+    return sr_dict({"headers": heads, "data": [cols.get(h) for h in heads]}, None, True)
+
+
 def table_from_columns(headers, data):
     """columnar sr_dict from ready-made columns (numpy arrays and/or device-resident column handles)."""
     return sr_dict({"headers": list(headers), "data": list(data)}, None, True)

@@ -37,6 +37,9 @@ class EmuBackend:
         a = np.zeros(max(int(nbytes), 256), dtype=np.uint8)
         return a.ctypes.data, a
 
+    def to_host(self, holder, nbytes):
+        return holder.view(np.uint8).reshape(-1)[:int(nbytes)]
+
     def stream(self):
         return None
 

@@ -31,6 +31,7 @@ static inline int cudaGetLastError() { return 0; }
 static inline int cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
 static inline int cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return 0; }
 static inline int cudaStreamSynchronize(cudaStream_t) { return 0; }
+#define cudaMemcpyHostToDevice 1
 #define cudaMemcpyDeviceToHost 2
 #define cudaMemcpyDeviceToDevice 3
 
