@@ -1736,6 +1736,8 @@ class Query:
             ptr, w = self.str_ptr(K, subj)
             fn = "str_find" if STRFIND_W else "str_find_bytes"
             cand = self.text_candidate(K, subj, pat.value)
+            if cand and fn == "str_find":
+                fn = "str_find_rare"
             return SScalar("bool", "(%ssdqlrt::%s(%s, %d, %s, %d) >= 0)" % (cand + " && " if cand else "", fn, ptr, w, cstr(pat.value), len(pat.value)), subj.prov)
         b = self.ev(e.inp2, env, K)
         if s in (XF.StartsWith, XF.EndsWith, XF.FirstIndex):
@@ -1748,7 +1750,7 @@ class Query:
             code = "sdqlrt::%s(%s, %d, %s, %d)" % (fn, ptr, w, cstr(b.value), len(b.value))
             cand = self.text_candidate(K, a, b.value) if s == XF.FirstIndex else None
             if cand:
-                code = "(%s ? %s : -1)" % (cand, code)
+                code = "(%s ? %s : -1)" % (cand, code.replace("sdqlrt::str_find(", "sdqlrt::str_find_rare("))
             if s == XF.FirstIndex:
                 return SScalar("i64", "(long long)" + K.let("int", code), a.prov)
             return SScalar("bool", code, a.prov)

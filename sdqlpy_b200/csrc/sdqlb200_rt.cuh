@@ -165,6 +165,7 @@ SDQL_DEV void stage_rows(unsigned char* dst, const unsigned char* col, i64 row0,
 
 #ifndef SDQLB200_EMU
 // primitives of the warp text scan (sdqlb200_textscan.cuh)
+#define TX_NOINLINE __device__ __noinline__
 SDQL_DEV int tx_lane() { return (int)(threadIdx.x & 31u); }
 SDQL_DEV void tx_syncwarp() { __syncwarp(); }
 SDQL_DEV unsigned tx_shfl_down(unsigned v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
@@ -628,6 +629,12 @@ SDQL_DEV int str_find(const unsigned char* s, int w, const char* pat, int plen) 
     const int r = str_find_bytes(s + i, w - i, pat, plen);
     return r < 0 ? -1 : r + i;
 }
+// out-of-line copy for call sites that run rarely (rows that passed the warp text scan): keeps the kernels small
+#ifndef SDQLB200_EMU
+__device__ __noinline__ int str_find_rare(const unsigned char* s, int w, const char* pat, int plen) { return str_find(s, w, pat, plen); }
+#else
+static inline int str_find_rare(const unsigned char* s, int w, const char* pat, int plen) { return str_find(s, w, pat, plen); }
+#endif
 SDQL_DEV bool str_starts(const unsigned char* s, int w, const char* pat, int plen) {  // varchar.h:99-111
     if (plen > w) return false;
     for (int j = 0; j < plen; ++j)

@@ -1,8 +1,8 @@
 // sdqlpy-b200 device runtime, part: warp text scan (included by sdqlb200_rt.cuh inside namespace sdqlrt).
 // Kept in a file of its own so that tests/emu/check_textscan.cpp can compile the 32-lane code path on the CPU (one
 // std::thread per lane, barrier-based shuffles) against the scalar definition.  Needs from the includer: SDQL_DEV, i64,
-// kStageRows, ld1<T>(), and -- unless SDQLB200_EMU -- tx_lane(), tx_syncwarp(), tx_shfl_down(), tx_atomic_or(),
-// tx_ldnc16().
+// kStageRows, ld1<T>(), and -- unless SDQLB200_EMU -- TX_NOINLINE, tx_lane(), tx_syncwarp(), tx_shfl_down(),
+// tx_atomic_or(), tx_ldnc16().
 // ---------------------------------------------------------------------------------------------
 // warp text scan: candidate rows for firstIndex / contains on a scanned string column.
 // The kStageRows rows a warp examines per iteration are one contiguous run of bytes.  All lanes stream the run with
@@ -40,6 +40,9 @@ SDQL_DEV unsigned text_load4(const unsigned char* src, size_t off, size_t total)
         if (off + j < total) v |= (unsigned)ld1(src + off + j) << (8 * j);
     return v;
 }
+#endif
+#ifndef SDQLB200_EMU
+TX_NOINLINE void text_mark(unsigned* mask, size_t row) { tx_atomic_or(mask + (row >> 5), 1u << (unsigned)(row & 31u)); }
 #endif
 template <int NP>
 SDQL_DEV void warp_text_scan(const unsigned char* col, i64 row0, i64 n, int W, const unsigned (&pat4)[NP], unsigned* mask) {
@@ -85,13 +88,17 @@ SDQL_DEV void warp_text_scan(const unsigned char* col, i64 row0, i64 n, int W, c
         }
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
-            if (!hit[p]) continue;  // rare: find the positions again and mark their rows
+            if (!hit[p]) continue;
+            // rare (a few percent of the chunks): find the positions again, one word at a time in a rolled loop -- the
+            // code stays small (the fully unrolled form made the kernel miss the instruction cache)
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                const unsigned lo = j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : w[3];
+                const unsigned hi = j == 0 ? w[1] : j == 1 ? w[2] : j == 2 ? w[3] : w[4];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const unsigned win = (j & 3) ? __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], 8 * (j & 3)) : w[j >> 2];
-                if (win == pat4[p] && off + j < bytes) {
-                    const unsigned r = (unsigned)((off + j) / (size_t)W);
-                    tx_atomic_or(mask + p * kTextWords + (r >> 5), 1u << (r & 31u));
+                for (int a = 0; a < 4; ++a) {
+                    const unsigned win = a ? __funnelshift_r(lo, hi, 8 * a) : lo;
+                    if (win == pat4[p] && off + 4 * j + a < bytes) text_mark(mask + p * kTextWords, (off + 4 * j + a) / (size_t)W);
                 }
             }
         }

@@ -16,6 +16,7 @@
 #include <vector>
 
 #define SDQL_DEV static inline
+#define TX_NOINLINE static inline
 namespace sdqlrt {
 typedef long long i64;
 constexpr int kLanes = 32, kVec = 4, kStageRows = kLanes * kVec;
