@@ -67,6 +67,10 @@ TEXTSCAN = os.environ.get("SDQLB200_TEXTSCAN", "1") != "0"
 # warp: ncu showed q12_k0's main loop executing with 13 of 32 lanes active and 2.5x the warp-level instructions of the
 # cardinality pass over the same rows (profiles/r01_q12_k0_main_*.txt; SF100: 15.0 ms vs 1.3 ms).
 RECONVERGE = os.environ.get("SDQLB200_RECONVERGE", "1") != "0"
+# probes of single-part tables with an int32 column value use 32-bit key arithmetic (sdqlrt::pack_key1 / tbl_find1): the
+# narrow lineitem scans are bound by instruction issue (~3 warp instructions per row, profiles/r01_q5_k5_narrow_*.txt),
+# most of them 64-bit key packing and the generic presence test
+PROBE32 = os.environ.get("SDQLB200_PROBE32", "1") != "0"
 COMPACT = os.environ.get("SDQLB200_COMPACT", "1") != "0"  # rows surviving a selective probe are queued and re-dealt to all lanes
 BITS_FILTER = os.environ.get("SDQLB200_BITS", "1") != "0"  # presence bitmaps in front of selective, probed tables
 COUNT_PASS = os.environ.get("SDQLB200_COUNT_PASS", "1") != "0"  # cardinality passes in front of selective table builds
@@ -1529,8 +1533,11 @@ class Query:
                 leaves = [leaves[i] for i in t.kept_pos]
             else:
                 raise CodegenError("%s: lookup key has %d parts, table key has %d" % (t.name, len(leaves), n_expected))
-        codes = [self.part_code(K, x)[0] for x in leaves]
+        pcs = [self.part_code(K, x) for x in leaves]
+        codes = [pc[0] for pc in pcs]
         ckey = ("lookup", t.name, tuple(codes))
+        fast1 = (PROBE32 and len(codes) == 1 and t.inner is None and len(t.parts) == 1 and t.parts[0][0] == "col"
+                 and pcs[0][1] and pcs[0][1][0] == "col")
         hit = None
         for scope in K.cse:
             if ckey in scope:
@@ -1538,7 +1545,9 @@ class Query:
         if hit is None:
             kk = K.tmp("lk")
             K.emit("unsigned long long %s = 0; bool %s_ok = true;" % (kk, kk))
-            for j, code in enumerate(codes):
+            if fast1:
+                K.emit("%s_ok = sdqlrt::pack_key1((int)(%s), c.%s_mn[0], c.%s_rng[0], %s);" % (kk, codes[0], t.name, t.name, kk))
+            for j, code in enumerate(codes if not fast1 else ()):
                 K.emit("%s_ok &= sdqlrt::pack_part(%s, c.%s_mn[%d], c.%s_rng[%d], c.%s_mul[%d], %s);" %
                        (kk, code, t.name, j, t.name, j, t.name, j, kk))
             keyprov = frozenset().union(*[x.prov for x in leaves]) if leaves else E
@@ -1548,7 +1557,10 @@ class Query:
                 sl = kk
             else:
                 sl = K.tmp("sl")
-                K.emit("const int %s = sdqlrt::tbl_find(c.%s, %s, %s_ok);" % (sl, t.name, kk, kk))
+                if fast1:
+                    K.emit("const int %s = sdqlrt::tbl_find1(c.%s, (unsigned)%s, %s_ok);" % (sl, t.name, kk, kk))
+                else:
+                    K.emit("const int %s = sdqlrt::tbl_find(c.%s, %s, %s_ok);" % (sl, t.name, kk, kk))
             hit = (sl, tok)
             K.cse[-1][ckey] = hit
         sl, tok = hit

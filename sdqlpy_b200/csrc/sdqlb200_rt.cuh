@@ -246,6 +246,34 @@ SDQL_DEV int tbl_find(const Tbl& t, u64 key, bool ok) {
     }
 }
 
+// Single-part keys whose part is an int32 column value (the common probe: a foreign key looked up in a table keyed by the
+// primary key): the packed key is the 32-bit offset from the build column's minimum, and the probe needs no 64-bit
+// multiply / modulo.  Same results as pack_part + tbl_find (a single-part table never has a first-part modulus).
+SDQL_DEV bool pack_key1(int x, i64 mn, i64 rng, u64& key) {
+    const int m = (int)mn;  // statistics of an int32 / dictionary-code column
+    const unsigned d = (unsigned)x - (unsigned)m;
+    key = d;
+    return x >= m && (u64)d < (u64)rng;
+}
+SDQL_DEV int tbl_find1(const Tbl& t, unsigned d, bool ok) {
+    if (!ok) return -1;
+    if (t.bits) {
+        stat(kStBitTests);
+        if (!((ld1(t.bits + (d >> 5)) >> (d & 31u)) & 1u)) return -1;
+    }
+    stat(kStFinds);
+    if (t.direct) { stat(kStFindSlots); return ld1(t.rep + d) != -1 ? (int)d : -1; }
+    const u64 key = d, m = (u64)t.cap - 1;
+    u64 h = hash64(key) & m;
+    for (;;) {
+        stat(kStFindSlots);
+        u64 k = ld1(t.keys + h);
+        if (k == key) return (int)h;
+        if (k == kEmpty) return -1;
+        h = (h + 1) & m;
+    }
+}
+
 // insert-or-find; `src` becomes the slot's representative if the slot is new.  -> slot
 SDQL_DEV int tbl_upsert(const Tbl& t, u64 key, int src, bool& is_new) {
     stat(kStUpserts);
