@@ -71,6 +71,11 @@ RECONVERGE = os.environ.get("SDQLB200_RECONVERGE", "1") != "0"
 # narrow lineitem scans are bound by instruction issue (~3 warp instructions per row, profiles/r01_q5_k5_narrow_*.txt),
 # most of them 64-bit key packing and the generic presence test
 PROBE32 = os.environ.get("SDQLB200_PROBE32", "1") != "0"
+# 32-bit row / group indices in the relation-scan loops (row ids are int32 everywhere else already: Tbl.rep, the hit
+# queues).  Opt-in: written after the round's GPU budget was spent, checked under emulation only; the host driver
+# refuses relations of more than 2'000'000'000 rows in such a build.  Static SASS of the scan loops shrinks (see
+# DESIGN.md section 4, "next round"); to be A/B'd on B200 with tools/build_variant.py idx32 SDQLB200_IDX32=1.
+IDX32 = os.environ.get("SDQLB200_IDX32", "0") == "1"
 COMPACT = os.environ.get("SDQLB200_COMPACT", "1") != "0"  # rows surviving a selective probe are queued and re-dealt to all lanes
 BITS_FILTER = os.environ.get("SDQLB200_BITS", "1") != "0"  # presence bitmaps in front of selective, probed tables
 COUNT_PASS = os.environ.get("SDQLB200_COUNT_PASS", "1") != "0"  # cardinality passes in front of selective table builds
@@ -454,6 +459,7 @@ class Kernel:
             # software-pipelined streaming loop: the next group's column loads are issued before the current
             # group is processed, so every thread keeps two groups (2 x 4 rows x all columns) in flight
             ety = {"i32": "int", "f64": "double", "code": "int"}
+            IT = "int" if IDX32 else "long long"  # type of row / row-group indices in this loop
             R = self.rows_per_thread()
             self.R = R
 
@@ -464,7 +470,7 @@ class Kernel:
                 o = []
                 for k in range(G):
                     o.append(ind + "{")
-                    o.append(ind + "    const long long j0 = (%s + %d * (long long)blockDim.x) << 2;" % (gvar, k))
+                    o.append(ind + "    const %s j0 = (%s + %d * (%s)blockDim.x) << 2;" % (IT, gvar, k, IT))
                     o.append(ind + "    if (j0 + 4 <= n) {")
                     for (col, rep), (arr, idx) in self.scan_cols.items():
                         dst = prefix + arr[2:]
@@ -476,7 +482,7 @@ class Kernel:
                             o.append(ind + "        %ssdqlrt::ld4(c.in%d + j0, %s);" % (cg, idx, d4))
                     o.append(ind + "    } else {")
                     o.append(ind + "        for (int u = 0; u < 4; ++u) {")
-                    o.append(ind + "            const long long ii = (j0 + u < n) ? j0 + u : n - 1;")
+                    o.append(ind + "            const %s ii = (j0 + u < n) ? j0 + u : n - 1;" % IT)
                     for (col, rep), (arr, idx) in self.scan_cols.items():
                         dst = prefix + arr[2:]
                         cg = self.count_guard(col, rep)
@@ -489,32 +495,33 @@ class Kernel:
                     o.append(ind + "}")
                 return o
 
-            L.append("    const long long n = c.n_%s;" % self.src[1])
-            L.append("    const long long ngrp = (n + 3) >> 2;")
-            L.append("    const long long gstride = (long long)gridDim.x * blockDim.x * %d;" % G)
-            L.append("    long long g = (long long)blockIdx.x * blockDim.x * %d + threadIdx.x;" % G)
+            L.append("    const %s n = %sc.n_%s;" % (IT, "(int)" if IDX32 else "", self.src[1]))
+            L.append("    const %s ngrp = (n + 3) >> 2;" % IT)
+            L.append("    const %s gstride = (%s)gridDim.x * blockDim.x * %d;" % (IT, IT, G))
+            L.append("    %s g = (%s)blockIdx.x * blockDim.x * %d + threadIdx.x;" % (IT, IT, G))
             loop_cond = "g < ngrp"
             if RECONVERGE:
-                loop_cond = "g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp"
+                loop_cond = "g - (%s)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp" % IT
             if self.body2 is not None:
-                loop_cond = "g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp"
+                loop_cond = "g - (%s)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp" % IT
                 L.append("    int* const wq = (int*)((unsigned char*)sm + c.%s_qo) + (threadIdx.x / sdqlrt::kLanes) * (sdqlrt::kLanes * %d);" %
                          (self.name, R + 1))
                 L.append("    const int lane_ = (int)(threadIdx.x & (sdqlrt::kLanes - 1));")
                 L.append("    int wcnt = 0;  // rows queued by this warp (the same value in every lane)")
             if self.byte_cols:
                 # every lane of a warp runs the same number of iterations (the warp stages its rows cooperatively)
-                loop_cond = "g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp"
+                loop_cond = "g - (%s)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp" % IT
                 boff = 0
                 for idx, w in self.byte_cols.items():
                     L.append("    unsigned char* const bs%d = (unsigned char*)sm + c.%s_bo + %du + (threadIdx.x / sdqlrt::kLanes) * %du;" %
                              (idx, self.name, 16 + boff, 128 * w))
                     boff += 1024 * w
-            stage = ["        sdqlrt::stage_rows(bs%d, c.in%d, (g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1))) << 2, n, %d);" % (idx, idx, w)
+            row0 = "(g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1))) << 2"  # first row of the warp's run (64-bit)
+            stage = ["        sdqlrt::stage_rows(bs%d, c.in%d, %s, n, %d);" % (idx, idx, row0, w)
                      for idx, w in self.byte_cols.items()]
             if self.text_cols:
                 # every lane of a warp runs the same number of iterations (the warp scans its rows' bytes cooperatively)
-                loop_cond = "g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp"
+                loop_cond = "g - (%s)(threadIdx.x & (sdqlrt::kLanes - 1)) < ngrp" % IT
                 toff = 0
                 for idx, (w, pats) in self.text_cols.items():
                     L.append("    unsigned* const tm%d = (unsigned*)((unsigned char*)sm + c.%s_to + %du) + (threadIdx.x / sdqlrt::kLanes) * (%d * sdqlrt::kTextWords);" %
@@ -522,8 +529,8 @@ class Kernel:
                     L.append("    const unsigned tp%d[%d] = {%s};" % (idx, len(pats), ", ".join(
                         "0x%08xu /* %s */" % (int.from_bytes(p_[:4].encode("latin1"), "little"), p_[:4].replace("*/", "")) for p_ in pats)))
                     toff += 256 * 4 * len(pats)  # (kBlock / kLanes) warps x kTextWords words: at most 256 words per pattern
-                    stage.append("        sdqlrt::warp_text_scan<%d>(c.in%d, (g - (long long)(threadIdx.x & (sdqlrt::kLanes - 1))) << 2, n, %d, tp%d, tm%d);" %
-                                 (len(pats), idx, w, idx, idx))
+                    stage.append("        sdqlrt::warp_text_scan<%d>(c.in%d, %s, n, %d, tp%d, tm%d);" %
+                                 (len(pats), idx, row0, w, idx, idx))
 
             def loop_head(cond):
                 if self.body2 is None:
@@ -538,7 +545,7 @@ class Kernel:
                 L.append("    if (g < ngrp)")
                 L += loads("r_", "g", "    ")
                 L += loop_head(loop_cond)
-                L.append("        const long long gn = g + gstride;")
+                L.append("        const %s gn = g + gstride;" % IT)
                 L.append("        if (gn < ngrp)")
                 L += loads("q_", "gn", "        ")
                 L += stage
@@ -546,21 +553,21 @@ class Kernel:
                 for (col, rep), (arr, idx) in self.scan_cols.items():
                     L.append("    %s %s[%d];" % (ety[rep], arr, R))
                 L += loop_head(loop_cond)
-                L.append("        const long long gn = g + gstride;")
+                L.append("        const %s gn = g + gstride;" % IT)
                 L += stage
-                L.append("        { const long long gp = g + %d * gstride; if (gp < ngrp) {" % PF_DIST)
+                L.append("        { const %s gp = g + %d * gstride; if (gp < ngrp) {" % (IT, PF_DIST))
                 for (col, rep), (arr, idx) in self.scan_cols.items():
                     cg = self.count_guard(col, rep)
                     for k in range(G):
                         if rep == "code":
-                            L.append("            %ssdqlrt::prefetch_l2((const char*)c.in%d + ((gp + %d * (long long)blockDim.x) << 2) * c.in%d_w);" % (cg, idx, k, idx))
+                            L.append("            %ssdqlrt::prefetch_l2((const char*)c.in%d + %s((gp + %d * (%s)blockDim.x) << 2) * c.in%d_w);" % (cg, idx, "(long long)" if IDX32 else "", k, IT, idx))
                         else:
-                            L.append("            %ssdqlrt::prefetch_l2(c.in%d + ((gp + %d * (long long)blockDim.x) << 2));" % (cg, idx, k))
+                            L.append("            %ssdqlrt::prefetch_l2(c.in%d + ((gp + %d * (%s)blockDim.x) << 2));" % (cg, idx, k, IT))
                 L.append("        } }")
                 L += loads("r_", "g", "        ")
             L.append("#pragma unroll")
             L.append("        for (int u = 0; u < %d; ++u) {" % R)
-            L.append("            const long long i = ((g + (u >> 2) * (long long)blockDim.x) << 2) + (u & 3);")
+            L.append("            const %s i = ((g + (u >> 2) * (%s)blockDim.x) << 2) + (u & 3);" % (IT, IT))
             if self.body2 is not None:
                 L.append("            bool pass_ = false;")
             L.append("            if (i < n) {")
@@ -1963,6 +1970,9 @@ def render_query(q):
         L.append("    c.n_%s = a->nrows[%d];" % (ar_, i))
     for i in range(len(q.consts)):
         L.append("    c.k%d = a->consts[%d];" % (i, i))
+    if IDX32:
+        for ar_ in q.args:
+            L.append("    if (c.n_%s > 2000000000ll) return sdqlhost::fail(SDQLB200_E_ARG, \"%s: relation %s has more rows than a 32-bit index build supports\");" % (ar_, n, ar_))
     nt = len(q.tables)
     L.append("    sdqlhost::TblRegion tr[%d];" % max(1, nt))
     for ti, t in enumerate(q.tables):

@@ -98,3 +98,35 @@ def test_forced_table_paths_match_reference(forced_module, q):
     gold = golden(0.01)
     got = forced_module.run(q, compact_db(0.01, rr.QUERY_ARGS[q]))
     assert compare(got, gold[q]) is None
+
+
+def test_opt_in_code_generator_switches_keep_results(tmp_path):
+    """switches that are off by default (SDQLB200_IDX32: 32-bit row indices) or that have an A/B partner build
+    (PROBE32 / RECONVERGE / TEXTSCAN off): the generated module must still reproduce the reference's outputs.  The code
+    generator reads its switches at import, hence the subprocess."""
+    import subprocess
+    import sys
+    script = r'''
+import os, sys
+sys.path[:0] = [%(root)r, %(root)r + "/tests", %(root)r + "/tests/emu", %(root)r + "/oracle"]
+import emu
+from compare import compare
+from sdqlpy_b200 import build, runtime
+from util import QUERY_SCRIPT, compact_db, golden
+import ref_runner as rr
+qs = ["q1", "q6", "q3", "q12", "q13", "q9", "q16", "q18"]
+text, _ = build.compile_source(open(QUERY_SCRIPT).read(), "queries.py", only=qs)
+cu = os.path.join(%(tmp)r, os.environ["TAG"] + ".cu")
+open(cu, "w").write(text)
+runtime.set_backend(emu.EmuBackend())
+mod = runtime.CompiledModule(emu.build_emu(cu, cu[:-3] + ".so"))
+for q in qs:
+    d = compare(mod.run(q, compact_db(0.01, rr.QUERY_ARGS[q])), golden(0.01)[q])
+    assert d is None, (q, d)
+print("ok")
+''' % {"root": os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tmp": str(tmp_path)}
+    for tag, env in (("idx32", {"SDQLB200_IDX32": "1"}),
+                     ("plain", {"SDQLB200_PROBE32": "0", "SDQLB200_RECONVERGE": "0", "SDQLB200_TEXTSCAN": "0"})):
+        e = dict(os.environ, TAG=tag, **env)
+        r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=e)
+        assert r.returncode == 0 and "ok" in r.stdout, (tag, r.stdout[-500:], r.stderr[-2000:])
