@@ -100,6 +100,25 @@ def test_forced_table_paths_match_reference(forced_module, q):
     assert compare(got, gold[q]) is None
 
 
+@pytest.mark.parametrize("q", QUERIES)
+def test_empty_relations_match_reference(emu_module, q):
+    """every relation empty: the reference's outputs (tests/golden/tpch_empty.json: empty sets, 0.0, Q14's 0/0 = NaN,
+    Q19's single all-zero record)"""
+    from util import cut_db
+    got = emu_module.run(q, cut_db(compact_db(0.01, rr.QUERY_ARGS[q]), rr.QUERY_ARGS[q], 0))
+    assert compare(got, golden("empty")[q]) is None
+
+
+@pytest.mark.parametrize("q", QUERIES)
+def test_ragged_relations_match_reference(emu_module, q):
+    """257 orders and their 1023 lineitems (no multiple of 4 / 32 / 128 rows), complete dimension tables"""
+    import json
+    from util import ROOT, cut_db
+    rows = json.load(open(os.path.join(ROOT, "tests", "golden", "tpch_ragged.json")))["rows"]
+    got = emu_module.run(q, cut_db(compact_db(0.01, rr.QUERY_ARGS[q]), rr.QUERY_ARGS[q], rows))
+    assert compare(got, golden("ragged")[q]) is None
+
+
 def test_opt_in_code_generator_switches_keep_results(tmp_path):
     """switches that are off by default (SDQLB200_IDX32: 32-bit row indices) or that have an A/B partner build
     (PROBE32 / RECONVERGE / TEXTSCAN off): the generated module must still reproduce the reference's outputs.  The code

@@ -39,6 +39,19 @@ def test_reference_module_sf05(mod, q):
     assert compare(got, want) is None
 
 
+@pytest.mark.parametrize("q", QUERIES)
+def test_edge_case_inputs(mod, q):
+    """empty relations, and 257 orders with their 1023 lineitems (row counts that are no multiple of 4 / 32 / 128):
+    outputs of the real reference in tests/golden/tpch_empty.json / tpch_ragged.json"""
+    import json
+    import os
+    from util import ROOT, cut_db
+    db = compact_db(0.01, rr.QUERY_ARGS[q])
+    assert compare(mod.run(q, cut_db(db, rr.QUERY_ARGS[q], 0)), golden("empty")[q]) is None
+    rows = json.load(open(os.path.join(ROOT, "tests", "golden", "tpch_ragged.json")))["rows"]
+    assert compare(mod.run(q, cut_db(db, rr.QUERY_ARGS[q], rows)), golden("ragged")[q]) is None
+
+
 @pytest.mark.parametrize("q", ["q1", "q6", "q3", "q12", "q19"])
 def test_reference_layout_inputs(mod, q):
     """the reference's own input layout (int64 / float64 / <U n numpy arrays) through the boundary."""

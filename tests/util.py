@@ -9,8 +9,22 @@ QUERIES = ["q%d" % i for i in range(1, 23)]
 QUERY_SCRIPT = os.path.join(ROOT, "sdqlpy_b200", "tpch", "queries.py")
 
 
+# "ragged" edge-case inputs (tests/golden/make_edge_golden.py): the first RAGGED_ORDERS orders of SF0.01 and exactly their
+# lineitems (row counts that are no multiple of 4 / 32 / 128), dimension tables complete -- referential integrity is
+# kept because the reference aborts on a missing key (uncaught phmap at())
+RAGGED_ORDERS = 257
+
+
+def ragged_rows(orders_first_col, lineitem_first_col):
+    """{table: rows to keep}: given the o_orderkey and l_orderkey columns (numpy arrays) of the full SF0.01 tables"""
+    last = orders_first_col[RAGGED_ORDERS - 1]
+    return {"orders": RAGGED_ORDERS, "lineitem": int((lineitem_first_col <= last).sum())}
+
+
 def golden(sf):
-    path = os.path.join(ROOT, "tests", "golden", "tpch_sf%s.json" % ("%g" % sf).replace(".", "p"))
+    """sf: a scale factor (tpch_sf0p01.json ..) or the tag of an edge-case file ("empty", "ragged")"""
+    tag = sf if isinstance(sf, str) else "sf%s" % ("%g" % sf).replace(".", "p")
+    path = os.path.join(ROOT, "tests", "golden", "tpch_%s.json" % tag)
     raw = json.load(open(path))
     out = {}
     for q, r in raw["queries"].items():
@@ -41,3 +55,21 @@ def ref_db(sf, query_args):
         if t not in g["t"]:
             g["t"][t] = g["g"].ref_table(t, [c for c, _ in SCHEMAS[t]])
     return [g["t"][t] for t in query_args]
+
+
+def cut_db(db, query_args, rows):
+    """the relations of ``db`` (compact or reference layout) cut to ``rows[table]`` rows (0 = empty relations)"""
+    from sdqlpy_b200.tpch.gen import Column
+    out = []
+    for t, rel in zip(query_args, db):
+        n = rows.get(t) if isinstance(rows, dict) else rows   # None: the whole relation
+        cut = []
+        for c in rel:
+            if c is None:
+                cut.append(None)
+            elif isinstance(c, Column):
+                cut.append(Column(c.name, c.kind, c.data[:n], c.dictionary, c.width))
+            else:
+                cut.append(c[:n])
+        out.append(cut)
+    return out
