@@ -97,6 +97,38 @@ def lineitem_columns(g, man, order_range):
     return g.columns("lineitem", need, order_range)
 
 
+def result_check(q, cols, result):
+    """size-independent properties of the bench query's result at the full bench size, against numpy reductions over the
+    host columns (outside every timed region): row counts and integer-valued sums exactly, fp64 sums within 1e-9
+    relative.  -> "ok" or a description of the first violated property (reported in the JSON line, never raised)."""
+    try:
+        ship = np.asarray(cols["l_shipdate"].data)
+        if q == "q1":
+            m = ship <= 19980902
+            rows = result.tuples()
+            if sum(r[-1] for r in rows) != int(m.sum()):
+                return "sum of count_order %d != %d qualifying rows" % (sum(r[-1] for r in rows), int(m.sum()))
+            qty = float(np.asarray(cols["l_quantity"].data)[m].sum())  # integer-valued: exact in any order
+            if sum(r[2] for r in rows) != qty:
+                return "sum of sum_qty %r != %r" % (sum(r[2] for r in rows), qty)
+            base = float(np.asarray(cols["l_extendedprice"].data)[m].sum())
+            got = sum(r[3] for r in rows)
+            if abs(got - base) > 1e-9 * abs(base):
+                return "sum of sum_base_price %r != %r" % (got, base)
+            groups = len(set(zip(np.asarray(cols["l_returnflag"].data)[m].tolist(), np.asarray(cols["l_linestatus"].data)[m].tolist())))
+            if len(rows) != groups:
+                return "%d groups != %d" % (len(rows), groups)
+            return "ok"
+        if q == "q6":
+            disc, qty = np.asarray(cols["l_discount"].data), np.asarray(cols["l_quantity"].data)
+            m = (ship >= 19940101) & (ship < 19950101) & (disc >= 0.05) & (disc <= 0.07) & (qty < 24.0)
+            want = float((np.asarray(cols["l_extendedprice"].data)[m] * disc[m]).sum())
+            return "ok" if abs(float(result) - want) <= 1e-9 * abs(want) else "revenue %r != %r" % (float(result), want)
+        return "no check for %s" % q
+    except Exception as ex:  # a broken checker must not cost the bench line
+        return "checker failed: %r" % (ex,)
+
+
 def ref_arm(args, nproc):
     """the reference's own CPU implementation of the path, all host threads, on a bounded sample."""
     import ref_runner as rr
@@ -302,6 +334,7 @@ def main():
                    "query -> result to host; %d steps; value = resident-layout bytes / time (same numerator as "
                    "'value' and as the reference arm)" % args.e2e_steps}
     runtime.STORE.enabled = True
+    checked = result_check(q, cols, r) if world == 1 else "not checked (N > 1: the host columns are this rank's partition)"
     out = {
         "metric": "tpch_%s_scan_throughput" % q, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -309,7 +342,7 @@ def main():
         "config": {"workload": workload, "query": q, "sf_per_gpu": args.sf, "rows_per_gpu": rows,
                    "bytes_per_row": bpr, "layout": bcols, "l2_policy": "inputs (%.2f GB per GPU) larger than L2" % (step_bytes / 1e9),
                    "latency_ms_device": float(np.mean(dev_ms)), "agg_tier": int(a.tier)},
-        "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "result_check": checked,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
