@@ -314,7 +314,7 @@ def main():
     runtime.STORE.enabled = False
     runtime.STORE.clear()
     fn = getattr(mod, q + "_compiled")
-    fn(db)
+    r = fn(db)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
