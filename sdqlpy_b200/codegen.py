@@ -83,6 +83,13 @@ IDX32 = os.environ.get("SDQLB200_IDX32", "0") == "1"
 # Changes the order of fp64 additions (still within the 1e-9 bar; the atomics' order is not fixed either).  Opt-in:
 # written after the round's GPU budget was spent, checked under emulation only.
 RUNAGG = os.environ.get("SDQLB200_RUNAGG", "0") == "1"
+# Tier 0 of a group-by (tiny key domain) with the thread-private accumulators in SHARED memory instead of registers: cell
+# (slot, field) of thread t lives at sm[(slot * nf + field) * kBlock + t] (conflict-free: consecutive lanes, consecutive
+# 8-byte words).  A row then updates only the nf cells of its slot (LDS + DADD + STS each) instead of running rcap x nf
+# predicated adds, and the kernel needs ~60 fewer registers: `q1_k0<0>` (the bench's dominant kernel) sits at 128
+# registers / 2 CTAs per SM / 16 warps per SM today with 32 % of its stall samples on long scoreboard.  Opt-in: written
+# after the round's GPU budget was spent, checked under emulation only.
+TIER0_SMEM = os.environ.get("SDQLB200_TIER0_SMEM", "0") == "1"
 COMPACT = os.environ.get("SDQLB200_COMPACT", "1") != "0"  # rows surviving a selective probe are queued and re-dealt to all lanes
 BITS_FILTER = os.environ.get("SDQLB200_BITS", "1") != "0"  # presence bitmaps in front of selective, probed tables
 COUNT_PASS = os.environ.get("SDQLB200_COUNT_PASS", "1") != "0"  # cardinality passes in front of selective table builds
@@ -956,9 +963,17 @@ class GroupSink(KeyedSink):
             # TIER 0: accumulators of every (slot, field) cell live in registers; the row's slot is matched against the
             # statically unrolled slot index (predicated adds, no shared-memory traffic, no atomics)
             K.emit("if (TIER == 0) {")
+            if TIER0_SMEM:
+                K.emit("    unsigned long long* const pc_ = pa_ + (int)%s * (%d * sdqlrt::kBlock);" % (kk, nf))
+                for j, (_, ct) in enumerate(t.fields):
+                    if ct == "f64":
+                        K.emit("    ((double*)pc_)[%d * sdqlrt::kBlock] += %s;" % (j, vals[j]))
+                    else:
+                        K.emit("    pc_[%d * sdqlrt::kBlock] += (unsigned long long)(%s);" % (j, vals[j]))
             for sl_ in range(self.rcap):  # unrolled here (scalar accumulators: nothing can end up in local memory)
-                upd = " ".join("ra%d_%d += %s;" % (j, sl_, ("(unsigned long long)(%s)" % vals[j]) if ct != "f64" else vals[j])
-                               for j, (_, ct) in enumerate(t.fields))
+                upd = "" if TIER0_SMEM else " ".join(
+                    "ra%d_%d += %s;" % (j, sl_, ("(unsigned long long)(%s)" % vals[j]) if ct != "f64" else vals[j])
+                    for j, (_, ct) in enumerate(t.fields))
                 K.emit("    if ((int)%s == %d) { %s rrep_%d = (int)%s; }" % (kk, sl_, upd, sl_, K.scan_var))
             K.emit("} else if (TIER == 1) {")
             K.emit("    const int sb = (int)%s * %d;" % (kk, nf))
@@ -1026,9 +1041,13 @@ class GroupSink(KeyedSink):
         self.rcap = max(1, min(8, 32 // nf))  # register tier: <= 8 groups and <= 32 accumulator cells per thread
         K.rcap = self.rcap
         K.pre.append("const long long ncap = c.%s.cap;" % t.name)
-        for j, (_, ct) in enumerate(t.fields):
-            K.pre.append("%s %s;" % ("double" if ct == "f64" else "unsigned long long",
-                                     ", ".join("ra%d_%d = 0" % (j, sl_) for sl_ in range(self.rcap))))
+        if TIER0_SMEM:
+            K.pre.append("unsigned long long* const pa_ = sm + threadIdx.x;  // this thread's cells: pa_[cell * kBlock]")
+            K.pre.append("if (TIER == 0) { for (int k = 0; k < %d; ++k) pa_[k * sdqlrt::kBlock] = 0; }" % (self.rcap * nf))
+        else:
+            for j, (_, ct) in enumerate(t.fields):
+                K.pre.append("%s %s;" % ("double" if ct == "f64" else "unsigned long long",
+                                         ", ".join("ra%d_%d = 0" % (j, sl_) for sl_ in range(self.rcap))))
         K.pre.append("int %s;" % ", ".join("rrep_%d = -1" % sl_ for sl_ in range(self.rcap)))
         K.pre.append("int* smrep = (int*)(sm + ncap * %d);" % nf)
         K.pre.append("if (TIER == 1) { for (long long k = threadIdx.x; k < ncap * %d; k += blockDim.x) sm[k] = 0; "
@@ -1046,10 +1065,13 @@ class GroupSink(KeyedSink):
                 P.append("    if (%d < ncap) {" % sl_)
                 P.append("        const int r = sdqlrt::block_max(rrep_%d);" % sl_)
                 for j, (_, ct) in enumerate(t.fields):
+                    acc = "ra%d_%d" % (j, sl_)
+                    if TIER0_SMEM:
+                        acc = ("((double*)pa_)[%d * sdqlrt::kBlock]" if ct == "f64" else "pa_[%d * sdqlrt::kBlock]") % (sl_ * nf + j)
                     if ct == "f64":
-                        P.append("        const double v%d = sdqlrt::block_sum(ra%d_%d);" % (j, j, sl_))
+                        P.append("        const double v%d = sdqlrt::block_sum(%s);" % (j, acc))
                     else:
-                        P.append("        const long long v%d = sdqlrt::block_sum((long long)ra%d_%d);" % (j, j, sl_))
+                        P.append("        const long long v%d = sdqlrt::block_sum((long long)%s);" % (j, acc))
                 P.append("        if (threadIdx.x == 0 && r >= 0) {")
                 P.append("            atomicMax(c.%s.rep + %d, r);" % (t.name, sl_))
                 for j, (_, ct) in enumerate(t.fields):
@@ -2045,7 +2067,11 @@ def render_query(q):
         if K.tiered:
             nf, tn = K.smem_nf, K.smem_tbl
             L.append("        const long long cap = c.%s.cap;" % tn)
-            L.append("        if (c.%s.direct && cap <= %d) tier_%s = 0;" % (tn, K.rcap, K.name))
+            if TIER0_SMEM:
+                L.append("        if (c.%s.direct && cap <= %d) { tier_%s = 0; sm_%s = (size_t)%d * sdqlrt::kBlock * 8; }" %
+                         (tn, K.rcap, K.name, K.name, K.rcap * nf))
+            else:
+                L.append("        if (c.%s.direct && cap <= %d) tier_%s = 0;" % (tn, K.rcap, K.name))
             L.append("        else if (c.%s.direct && cap * (%d * 8 + 4) <= 65536) { tier_%s = 1; sm_%s = (size_t)cap * (%d * 8 + 4); }" %
                      (tn, nf, K.name, K.name, nf))
             fn = "(tier_%s == 0 ? (const void*)%s<0> : tier_%s == 1 ? (const void*)%s<1> : (const void*)%s<2>)" % (
