@@ -970,8 +970,9 @@ class GroupSink(KeyedSink):
                         K.emit("    ((double*)pc_)[%d * sdqlrt::kBlock] += %s;" % (j, vals[j]))
                     else:
                         K.emit("    pc_[%d * sdqlrt::kBlock] += (unsigned long long)(%s);" % (j, vals[j]))
-            for sl_ in range(self.rcap):  # unrolled here (scalar accumulators: nothing can end up in local memory)
-                upd = "" if TIER0_SMEM else " ".join(
+                K.emit("    pr_[(int)%s * sdqlrt::kBlock] = (int)%s;" % (kk, K.scan_var))
+            for sl_ in range(self.rcap if not TIER0_SMEM else 0):  # unrolled here (scalar accumulators: nothing can end up in local memory)
+                upd = " ".join(
                     "ra%d_%d += %s;" % (j, sl_, ("(unsigned long long)(%s)" % vals[j]) if ct != "f64" else vals[j])
                     for j, (_, ct) in enumerate(t.fields))
                 K.emit("    if ((int)%s == %d) { %s rrep_%d = (int)%s; }" % (kk, sl_, upd, sl_, K.scan_var))
@@ -1043,12 +1044,15 @@ class GroupSink(KeyedSink):
         K.pre.append("const long long ncap = c.%s.cap;" % t.name)
         if TIER0_SMEM:
             K.pre.append("unsigned long long* const pa_ = sm + threadIdx.x;  // this thread's cells: pa_[cell * kBlock]")
-            K.pre.append("if (TIER == 0) { for (int k = 0; k < %d; ++k) pa_[k * sdqlrt::kBlock] = 0; }" % (self.rcap * nf))
+            K.pre.append("int* const pr_ = (int*)(sm + %d * sdqlrt::kBlock) + threadIdx.x;  // ... and its representative rows" % (self.rcap * nf))
+            K.pre.append("if (TIER == 0) { for (int k = 0; k < %d; ++k) pa_[k * sdqlrt::kBlock] = 0; "
+                         "for (int k = 0; k < %d; ++k) pr_[k * sdqlrt::kBlock] = -1; }" % (self.rcap * nf, self.rcap))
         else:
             for j, (_, ct) in enumerate(t.fields):
                 K.pre.append("%s %s;" % ("double" if ct == "f64" else "unsigned long long",
                                          ", ".join("ra%d_%d = 0" % (j, sl_) for sl_ in range(self.rcap))))
-        K.pre.append("int %s;" % ", ".join("rrep_%d = -1" % sl_ for sl_ in range(self.rcap)))
+        if not TIER0_SMEM:
+            K.pre.append("int %s;" % ", ".join("rrep_%d = -1" % sl_ for sl_ in range(self.rcap)))
         K.pre.append("int* smrep = (int*)(sm + ncap * %d);" % nf)
         K.pre.append("if (TIER == 1) { for (long long k = threadIdx.x; k < ncap * %d; k += blockDim.x) sm[k] = 0; "
                      "for (long long k = threadIdx.x; k < ncap; k += blockDim.x) smrep[k] = -1; __syncthreads(); }" % nf)
@@ -1063,7 +1067,7 @@ class GroupSink(KeyedSink):
             P.append("if (TIER == 0) {")
             for sl_ in range(self.rcap):
                 P.append("    if (%d < ncap) {" % sl_)
-                P.append("        const int r = sdqlrt::block_max(rrep_%d);" % sl_)
+                P.append("        const int r = sdqlrt::block_max(%s);" % (("pr_[%d * sdqlrt::kBlock]" % sl_) if TIER0_SMEM else "rrep_%d" % sl_))
                 for j, (_, ct) in enumerate(t.fields):
                     acc = "ra%d_%d" % (j, sl_)
                     if TIER0_SMEM:
@@ -2068,8 +2072,8 @@ def render_query(q):
             nf, tn = K.smem_nf, K.smem_tbl
             L.append("        const long long cap = c.%s.cap;" % tn)
             if TIER0_SMEM:
-                L.append("        if (c.%s.direct && cap <= %d) { tier_%s = 0; sm_%s = (size_t)%d * sdqlrt::kBlock * 8; }" %
-                         (tn, K.rcap, K.name, K.name, K.rcap * nf))
+                L.append("        if (c.%s.direct && cap <= %d) { tier_%s = 0; sm_%s = (size_t)%d * sdqlrt::kBlock * 8 + (size_t)%d * sdqlrt::kBlock * 4; }" %
+                         (tn, K.rcap, K.name, K.name, K.rcap * nf, K.rcap))
             else:
                 L.append("        if (c.%s.direct && cap <= %d) tier_%s = 0;" % (tn, K.rcap, K.name))
             L.append("        else if (c.%s.direct && cap * (%d * 8 + 4) <= 65536) { tier_%s = 1; sm_%s = (size_t)cap * (%d * 8 + 4); }" %
