@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--variants", default="default,legacy")
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--device-gen", action="store_true", help="lineitem / orders generated on the GPU (as tools/run_tpch.py): "
+                    "no host generation of the fact tables, SF100 fits one GPU")
     a = ap.parse_args()
     import ref_runner as rr
     from compare import compare
@@ -33,6 +35,10 @@ def main():
             os.path.join(ROOT, "gpurun_variants", v + ".so")
         mods[v] = runtime.CompiledModule(so)
     g = TPCH(a.sf)
+    dg = None
+    if a.device_gen:
+        from sdqlpy_b200.tpch.gen_device import DeviceTPCH
+        dg = DeviceTPCH(a.sf)
     tabs, report = {}, []
     for q in a.queries.split(","):
         base = None
@@ -46,7 +52,8 @@ def main():
                               {x.split(":")[3] for _, x in man["result"] if x.startswith("str:") and x.split(":")[2] == arg and len(x.split(":")) > 3})
                 key = (t, tuple(need))
                 if key not in tabs:
-                    cols = g.columns(t, need + [SCHEMAS[t][0][0]])
+                    src = dg if (dg is not None and t in ("lineitem", "orders")) else g
+                    cols = src.columns(t, need + [SCHEMAS[t][0][0]])
                     tabs[key] = [cols.get(c) for c, _ in SCHEMAS[t]]
                 db.append(tabs[key])
             res = mod.run(q, db)
@@ -70,6 +77,11 @@ def main():
             report.append(row)
         tabs.clear()
         runtime.STORE.clear()
+        if dg is not None:  # per-query workspaces and fact tables: the next query may need a very different size
+            for mod in mods.values():
+                mod.ws, mod.ws_bytes = None, 0
+            import torch
+            torch.cuda.empty_cache()
     if a.out:
         json.dump(report, open(a.out, "w"), indent=1)
 
