@@ -90,6 +90,24 @@ RUNAGG = os.environ.get("SDQLB200_RUNAGG", "0") == "1"
 # registers / 2 CTAs per SM / 16 warps per SM today with 32 % of its stall samples on long scoreboard.  Opt-in: written
 # after the round's GPU budget was spent, checked under emulation only.
 TIER0_SMEM = os.environ.get("SDQLB200_TIER0_SMEM", "0") == "1"
+# Early materialisation of the payload of build tables whose value expression itself contains lookups (a join chain:
+# Q9's partsupp entries carry the supplier's nation, found through two more tables): the fields consumers read are
+# evaluated ONCE, by the build kernel when it claims a slot, and stored in 8-byte arrays next to the slot; a consumer
+# then needs one load per field instead of re-walking the chain at the representative row (find + representative row +
+# gather per hop).  Opt-in: written after the round's GPU budget was spent, checked under emulation only (where the
+# counting build shows the data-dependent accesses drop, tests/test_stats.py).
+MATERIALISE = os.environ.get("SDQLB200_MATERIALISE", "0") == "1"
+
+
+def contains_lookup(e):
+    """does the IR expression contain a dictionary lookup?"""
+    if isinstance(e, ir.DicLookupExpr):
+        return True
+    if isinstance(e, ir.Expr):
+        return any(contains_lookup(x) for x in vars(e).values())
+    if isinstance(e, (list, tuple)):
+        return any(contains_lookup(x) for x in e)
+    return False
 COMPACT = os.environ.get("SDQLB200_COMPACT", "1") != "0"  # rows surviving a selective probe are queued and re-dealt to all lanes
 BITS_FILTER = os.environ.get("SDQLB200_BITS", "1") != "0"  # presence bitmaps in front of selective, probed tables
 COUNT_PASS = os.environ.get("SDQLB200_COUNT_PASS", "1") != "0"  # cardinality passes in front of selective table builds
@@ -212,6 +230,8 @@ class TableDesc:
         self.inner = None       # nested dict value: (n_outer_parts, [inner stats], inner key template SValue)
         self.probed = False     # looked up by some kernel (tbl_find): candidates for a presence filter
         self.distinct_of = None
+        self.mat = None         # early materialisation: OrderedDict field name (None = scalar value) -> (array index, leaf)
+        self.mat_names = None   # ... field names of the value record (None: the value is a single leaf)
 
     # -- element access ---------------------------------------------------------------------
     def src_elem(self, K, idx, prov=E):
@@ -265,6 +285,31 @@ class TableDesc:
             if self.scalar_value or self.count_only:
                 return vals[0][1]
             return SRec(vals)
+        if self.mat is not None:
+            # The value is evaluated symbolically in a scratch kernel (its code is thrown away) exactly as the late path
+            # would: the leaves carry the provenance / determination marks the functional-dependency minimisation of
+            # group keys needs (Q10 groups by seven fields of such a value).  Each leaf a consumer touches is then
+            # re-labelled to read the slot's array instead.
+            # one scratch kernel per consumer kernel: repeated lookups of the same entry (one per field access in the
+            # source) share their nested lookups -- and thereby their tokens -- through its CSE table, as they do on the
+            # late path through the consumer's own
+            Kd = K.__dict__.get("mat_scratch")
+            if Kd is None:
+                Kd = K.mat_scratch = Kernel(q, K.name + "_scratch", K.src)
+            keycode = None
+            if token is not None:
+                kv = flatten(Kd, self.key_fn(Kd, "0", prov))
+                if len(kv) == 1 and hasattr(kv[0], "code"):
+                    keycode = kv[0].code
+                elif len(kv) == 1 and kv[0].kind == "ref":
+                    keycode = ("ref", kv[0].arg, kv[0].col, kv[0].row)
+            v = mark(Kd, self.val_fn(Kd, "0", prov), prov, keycode, token)
+
+            def leaf(name):
+                return lambda: self.mat_leaf(name, sl, unwrap(v.field(Kd, name) if name is not None else v))
+            if self.mat_names is None:
+                return leaf(None)()
+            return SRec([(n, leaf(n)) for n in self.mat_names])
         rp = K.let("int", "sdqlrt::rep_of(c.%s, %s)" % (self.name, slot))
         keycode = None
         if token is not None:
@@ -275,6 +320,45 @@ class TableDesc:
                 keycode = ("ref", kv[0].arg, kv[0].col, kv[0].row)
         v = self.val_fn(K, rp, prov)
         return mark(K, v, prov, keycode, token)
+
+
+def _mat_template(v):
+    """kind of a materialised leaf, from a scratch evaluation of the value expression"""
+    v = unwrap(v)
+    if isinstance(v, SScalar):
+        return ("scalar", v.ctype, v.stats)
+    if isinstance(v, SStr) and v.kind == "ref":
+        return ("ref", v.arg, v.col, v.width)
+    if isinstance(v, SStr) and v.kind == "codeval":
+        return ("codeval", v.arg, v.col)
+    return None
+
+
+def _mat_leaf(self, name, sl, x):
+    """field ``name`` of the materialised value in slot ``sl``.  ``x`` = the leaf as the late path would compute it (from
+    a scratch evaluation): its marks are kept, its code is replaced by a load from the slot's array.  Registers the
+    field: the build kernel stores it (Query.splice_materialised)."""
+    tmpl = _mat_template(x)
+    if tmpl is None:
+        raise CodegenError("%s: field %r cannot be materialised" % (self.name, name))
+    if name not in self.mat:
+        j = len(self.fields)
+        self.fields.append((name, "f64" if (tmpl[0] == "scalar" and tmpl[1] == "f64") else "i64"))
+        self.mat[name] = (j, tmpl)
+    j, tmpl = self.mat[name]
+    code = "sdqlrt::ldg1(c.%s_a%d + %s)" % (self.name, j, sl)
+    if tmpl[0] == "scalar":
+        return SScalar(x.ctype, "(%s != 0)" % code if x.ctype == "bool" else code, x.prov, x.det, x.stats)
+    d = dict(x.__dict__)
+    kind = d.pop("kind")
+    if kind == "ref":
+        d["row"], d["scan"] = "(int)" + code, False
+    else:
+        d["code"] = "(int)" + code
+    return SStr(kind, **d)
+
+
+TableDesc.mat_leaf = _mat_leaf
 
 
 def leaf_kind(x):
@@ -904,7 +988,17 @@ class BuildSink(KeyedSink):
         K, t = self.K, self.t
         self.count_open()
         kk = self.pack(t, self.setup_key(t, d.k))
-        K.emit("if (%s_ok) { bool nw; sdqlrt::tbl_upsert(c.%s, %s, (int)%s, nw); }" % (kk, t.name, kk, K.scan_var))
+        if t.mat is not None:
+            # the slot's claimant stores the payload fields consumers ask for (filled in by Query.splice_materialised)
+            K.open_if("%s_ok" % kk)
+            K.emit("bool nw; const int slm_ = sdqlrt::tbl_upsert(c.%s, %s, (int)%s, nw);" % (t.name, kk, K.scan_var))
+            K.open_if("nw")
+            K.emit("/*MATERIALISE %s*/" % t.name)
+            t.mat_site = (K, K.depth, K.scan_var)
+            K.close()
+            K.close()
+        else:
+            K.emit("if (%s_ok) { bool nw; sdqlrt::tbl_upsert(c.%s, %s, (int)%s, nw); }" % (kk, t.name, kk, K.scan_var))
         self.count_close()
 
     def finish(self):
@@ -1381,6 +1475,40 @@ class Query:
             raise CodegenError("unsupported result value %s" % type(v).__name__)
         self.add_kernel(K)
 
+    def splice_materialised(self):
+        """early materialisation: now that every consumer has registered the payload fields it reads, the build kernels
+        get the code that evaluates those fields for the claiming row and stores them in the slot's arrays"""
+        for t in self.tables:
+            if t.mat is None or getattr(t, "mat_spliced", False):
+                continue
+            t.mat_spliced = True
+            K, depth, row = t.mat_site
+            marker = "/*MATERIALISE %s*/" % t.name
+            where = [(lst, i) for lst in (K.body, K.body2 or []) for i, x in enumerate(lst) if x.strip() == marker]
+            if not t.mat:
+                for lst, i in where:
+                    lst[i] = ""
+                continue
+            saved = (K.body, K.cse, K.depth, K.scan_var)
+            K.body, K.cse, K.depth, K.scan_var = [], [{}], depth, row
+            v = unwrap(t.val_fn(K, row))
+            for name, (j, tmpl) in t.mat.items():
+                x = unwrap(v.field(K, name) if name is not None else v)
+                if tmpl[0] == "scalar":
+                    code = x.code if tmpl[1] != "f64" else "__double_as_longlong(%s)" % x.code
+                    if tmpl[1] == "f64":
+                        K.emit("c.%s_a%d[slm_] = %s;" % (t.name, j, x.code))
+                    else:
+                        K.emit("c.%s_a%d[slm_] = (long long)(%s);" % (t.name, j, code))
+                elif tmpl[0] == "ref":
+                    K.emit("c.%s_a%d[slm_] = (long long)(%s);" % (t.name, j, x.row if not x.scan else row))
+                else:
+                    K.emit("c.%s_a%d[slm_] = (long long)(%s);" % (t.name, j, self.str_code(K, x)))
+            code = K.body
+            K.body, K.cse, K.depth, K.scan_var = saved
+            for lst, i in where:
+                lst[i:i + 1] = code
+
     def materialise_table(self, t):
         K = Kernel(self, "%s_fin" % self.name, ("tbl", t))
         elem = SPair(t.key_at(K, "i"), t.value_at(K, "i", None))
@@ -1507,7 +1635,7 @@ class Query:
         if K.sink is None:
             K.sink = self.make_sink(K, v)
             if isinstance(K.sink, (BuildSink, GroupSink)):
-                self.bind_table_fns(K, K.sink.t, e, env)
+                self.bind_table_fns(K, K.sink.t, e, env, allow_mat=isinstance(K.sink, BuildSink))
                 if K.depth > 0 and K.src[0] in ("rel", "tbl") and COUNT_PASS:
                     K.enable_count()
         K.sink.produce(v)
@@ -1517,7 +1645,7 @@ class Query:
                 if sub is not None and sub.t.key_fn is None:
                     self.bind_table_fns(K, sub.t, fe, env)
 
-    def bind_table_fns(self, K, t, e, env):
+    def bind_table_fns(self, K, t, e, env, allow_mat=False):
         """closures that re-evaluate the key / value expression of a produced {k: v} at a given source index."""
         S = K.S
         q = self
@@ -1543,6 +1671,21 @@ class Query:
             return q.ev(vexpr, env2, K2)
 
         t.key_fn, t.val_fn = key_fn, val_fn
+        if MATERIALISE and allow_mat and K.src[0] == "rel" and PIPELINE != "tma" and contains_lookup(vexpr):
+            # shape and leaf kinds of the value from a scratch evaluation (its code is thrown away)
+            Kd = Kernel(q, K.name + "_scratch", K.src)
+            Kd.S, Kd.root_env, Kd.row_var = K.S, K.root_env, K.row_var
+            try:
+                v = unwrap(val_fn(Kd, "0"))
+            except CodegenError:
+                return
+            if isinstance(v, (SRec, SRow)):
+                items = v.items(Kd)
+                names, tmpls = [n for n, _ in items], {n: _mat_template(x) for n, x in items}
+            else:
+                names, tmpls = None, {None: _mat_template(v)}
+            if any(x is not None for x in tmpls.values()):
+                t.mat, t.mat_names, t.mat_templates = OrderedDict(), names, tmpls
 
     def nested_sum(self, S, env, K):
         d = self.ev(S.dictExpr, env, K)
@@ -2000,6 +2143,7 @@ def render_query(q):
         L.append("    long long* res%d;" % j)
     L.append("};")
     L.append("")
+    q.splice_materialised()
     for K in q.kernels:
         L.append(K.render())
         L.append("")

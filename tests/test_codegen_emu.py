@@ -121,7 +121,8 @@ def test_ragged_relations_match_reference(emu_module, q):
 
 def test_opt_in_code_generator_switches_keep_results(tmp_path):
     """switches that are off by default (SDQLB200_IDX32: 32-bit row indices, SDQLB200_RUNAGG: run aggregation in front of
-    the global-tier atomics, SDQLB200_TIER0_SMEM: thread-private tier-0 accumulators in shared memory) or that have an A/B partner build
+    the global-tier atomics, SDQLB200_TIER0_SMEM: thread-private tier-0 accumulators in shared memory, SDQLB200_MATERIALISE: payloads of
+    join-chain build tables stored next to the slot) or that have an A/B partner build
     (PROBE32 / RECONVERGE / TEXTSCAN off): the generated module must still reproduce the reference's outputs.  The code
     generator reads its switches at import, hence the subprocess."""
     import subprocess
@@ -134,7 +135,7 @@ from compare import compare
 from sdqlpy_b200 import build, runtime
 from util import QUERY_SCRIPT, compact_db, golden
 import ref_runner as rr
-qs = ["q1", "q4", "q6", "q3", "q12", "q13", "q9", "q15", "q16", "q18", "q21", "q22"]
+qs = ["q1", "q2", "q4", "q5", "q6", "q3", "q7", "q10", "q12", "q13", "q9", "q15", "q16", "q18", "q21", "q22"]
 text, _ = build.compile_source(open(QUERY_SCRIPT).read(), "queries.py", only=qs)
 cu = os.path.join(%(tmp)r, os.environ["TAG"] + ".cu")
 open(cu, "w").write(text)
@@ -145,7 +146,7 @@ for q in qs:
     assert d is None, (q, d)
 print("ok")
 ''' % {"root": os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tmp": str(tmp_path)}
-    for tag, env in (("idx32", {"SDQLB200_IDX32": "1"}), ("runagg", {"SDQLB200_RUNAGG": "1"}), ("tier0smem", {"SDQLB200_TIER0_SMEM": "1"}),
+    for tag, env in (("idx32", {"SDQLB200_IDX32": "1"}), ("runagg", {"SDQLB200_RUNAGG": "1"}), ("tier0smem", {"SDQLB200_TIER0_SMEM": "1"}), ("mat", {"SDQLB200_MATERIALISE": "1"}),
                      ("plain", {"SDQLB200_PROBE32": "0", "SDQLB200_RECONVERGE": "0", "SDQLB200_TEXTSCAN": "0"})):
         e = dict(os.environ, TAG=tag, **env)
         r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=e)
