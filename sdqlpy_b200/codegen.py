@@ -97,6 +97,9 @@ TIER0_SMEM = os.environ.get("SDQLB200_TIER0_SMEM", "0") == "1"
 # gather per hop).  Opt-in: written after the round's GPU budget was spent, checked under emulation only (where the
 # counting build shows the data-dependent accesses drop, tests/test_stats.py).
 MATERIALISE = os.environ.get("SDQLB200_MATERIALISE", "0") == "1"
+# the insert side of PROBE32: keys of single-part tables over an int32 column are packed with 32-bit arithmetic in the
+# build / group-by kernels too (sdqlrt::pack_key1).  Opt-in, emulation-checked only.
+PACK32 = os.environ.get("SDQLB200_PACK32", "0") == "1"
 
 
 def contains_lookup(e):
@@ -971,6 +974,9 @@ class KeyedSink:
         K = self.K
         kk = K.tmp("kk")
         K.emit("unsigned long long %s = 0; bool %s_ok = true;" % (kk, kk))
+        if PACK32 and len(codes) == 1 and len(t.parts) == 1 and t.parts[0][0] == "col" and t.inner is None:
+            K.emit("%s_ok = sdqlrt::pack_key1((int)(%s), c.%s_mn[0], c.%s_rng[0], %s);" % (kk, codes[0], t.name, t.name, kk))
+            return kk
         for j, code in enumerate(codes):
             K.emit("%s_ok &= sdqlrt::pack_part(%s, c.%s_mn[%d], c.%s_rng[%d], c.%s_mul[%d], %s);" %
                    (kk, code, t.name, j, t.name, j, t.name, j, kk))

@@ -146,7 +146,7 @@ for q in qs:
     assert d is None, (q, d)
 print("ok")
 ''' % {"root": os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tmp": str(tmp_path)}
-    for tag, env in (("idx32", {"SDQLB200_IDX32": "1"}), ("runagg", {"SDQLB200_RUNAGG": "1"}), ("tier0smem", {"SDQLB200_TIER0_SMEM": "1"}), ("mat", {"SDQLB200_MATERIALISE": "1"}),
+    for tag, env in (("idx32", {"SDQLB200_IDX32": "1"}), ("runagg", {"SDQLB200_RUNAGG": "1"}), ("tier0smem", {"SDQLB200_TIER0_SMEM": "1"}), ("mat", {"SDQLB200_MATERIALISE": "1"}), ("pack32", {"SDQLB200_PACK32": "1"}),
                      ("plain", {"SDQLB200_PROBE32": "0", "SDQLB200_RECONVERGE": "0", "SDQLB200_TEXTSCAN": "0"})):
         e = dict(os.environ, TAG=tag, **env)
         r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=e)

@@ -10,3 +10,4 @@ python tools/build_variant.py runagg    ONLY=all SDQLB200_RUNAGG=1
 python tools/build_variant.py tier0smem ONLY=all SDQLB200_TIER0_SMEM=1
 python tools/build_variant.py next3     ONLY=all SDQLB200_TIER0_SMEM=1 SDQLB200_IDX32=1 SDQLB200_RUNAGG=1
 python tools/build_variant.py mat       ONLY=all SDQLB200_MATERIALISE=1
+python tools/build_variant.py pack32    ONLY=all SDQLB200_PACK32=1
