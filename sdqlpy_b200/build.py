@@ -79,8 +79,8 @@ def out_paths(script_path):
     return os.path.join(d, stem + "_compiled.cu"), os.path.join(d, stem + "_compiled.so")
 
 
-def nvcc(cu, so, verbose=False, defines=()):
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-I", CSRC, "-I", INC, cu, "-o", so]
+def nvcc(cu, so, verbose=False, defines=(), libs=()):
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-I", CSRC, "-I", INC, cu, "-o", so] + list(libs)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout[-4000:] + r.stderr[-8000:])
@@ -127,6 +127,20 @@ def compile_tbl(force=False):
     return nvcc(src, so)
 
 
+def compile_comm(force=False):
+    """csrc/sdqlb200_comm.cu -> sdqlpy_b200/_build/libsdqlb200_comm.so (cross-GPU merges: NVLink peer-memory all-reduce,
+    NCCL all-reduce, hash all-to-all; NCCL itself is bound at run time with dlopen)."""
+    src = os.path.join(CSRC, "sdqlb200_comm.cu")
+    out_dir = os.path.join(PKG, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libsdqlb200_comm.so")
+    deps = [src, os.path.join(INC, "sdqlb200_comm.h"), os.path.join(INC, "sdqlb200.h"), os.path.join(CSRC, "sdqlb200_rt.cuh"),
+            os.path.join(CSRC, "sdqlb200_host.h")]
+    if not force and os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps):
+        return so
+    return nvcc(src, so, libs=["-ldl"])
+
+
 def compile_file(script_path, force=False, verbose=False):
     """generate + build the module of one query script; returns the .so path."""
     cu, so = out_paths(script_path)
@@ -141,12 +155,47 @@ def compile_file(script_path, force=False, verbose=False):
     deps = [os.path.join(CSRC, f) for f in ("sdqlb200_rt.cuh", "sdqlb200_textscan.cuh", "sdqlb200_host.h")] + [os.path.join(INC, "sdqlb200.h")]
     fresh = (os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == digest
              and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps))
+    write_stub(script_path)
     if fresh and not force:
         return so
     open(cu, "w").write(text)
     nvcc(cu, so, verbose)
     open(stamp, "w").write(digest)
     return so
+
+
+STUB = '''# GENERATED by sdqlpy_b200.build -- do not edit.
+# The module the reference's dispatcher imports for %(script)s:  mod = __import__("%(stem)s_compiled");
+# getattr(mod, "<fn>_compiled")(db)  (sdqlpy/sdql_lib.py:401-424; method table sdql_compiler.py:751-777).  It forwards to
+# the sm_100a module %(so)s through the C ABI of include/sdqlb200.h; results come back as ``fastd`` objects with the
+# reference's size / print / to_dict / get / set / from_dict surface (fastd.py:31-51).
+import os as _os
+import sys as _sys
+
+_here = _os.path.dirname(_os.path.abspath(__file__))
+_pkg_parent = %(pkg_parent)r
+if _pkg_parent not in _sys.path:
+    _sys.path.insert(0, _pkg_parent)
+from sdqlpy_b200 import runtime as _rt  # noqa: E402
+
+_mod = _rt.load_compiled(_os.path.join(_here, %(script_name)r))
+for _q in _mod.queries:
+    globals()[_q + "_compiled"] = _rt.stub_entry(_mod, _q)
+'''
+
+
+def write_stub(script_path):
+    """<dir>/<script>_compiled.py: makes the compiled module importable under the name the UNMODIFIED reference wrapper
+    looks up (the reference installs its extension into site-packages, fast_dict_generator.py:163-165; a script's own
+    directory is on sys.path just as well)."""
+    script_path = os.path.abspath(script_path)
+    stem = os.path.splitext(os.path.basename(script_path))[0]
+    path = os.path.join(os.path.dirname(script_path), stem + "_compiled.py")
+    text = STUB % {"script": os.path.basename(script_path), "stem": stem, "so": os.path.basename(out_paths(script_path)[1]),
+                   "pkg_parent": ROOT, "script_name": os.path.basename(script_path)}
+    if not os.path.exists(path) or open(path).read() != text:
+        open(path, "w").write(text)
+    return path
 
 
 if __name__ == "__main__":

@@ -72,45 +72,21 @@ RECONVERGE = os.environ.get("SDQLB200_RECONVERGE", "1") != "0"
 # most of them 64-bit key packing and the generic presence test
 PROBE32 = os.environ.get("SDQLB200_PROBE32", "1") != "0"
 # 32-bit row / group indices in the relation-scan loops (row ids are int32 everywhere else already: Tbl.rep, the hit
-# queues).  Opt-in: written after the round's GPU budget was spent, checked under emulation only; the host driver
-# refuses relations of more than 2'000'000'000 rows in such a build.  Static SASS of the scan loops shrinks (see
-# DESIGN.md section 4, "next round"); to be A/B'd on B200 with tools/build_variant.py idx32 SDQLB200_IDX32=1.
-IDX32 = os.environ.get("SDQLB200_IDX32", "0") == "1"
-# Run aggregation in the global tier of a group-by over a scanned relation: consecutive rows of a thread with the same
-# packed key are added up in registers and reach the table as ONE insert-or-find + one atomic per field.  lineitem is
-# clustered by l_orderkey (4 lines per order on average), so group-bys keyed by it (Q18's and Q21's first passes: 600 M
-# rows each at SF100) issue ~2.3x fewer atomics, all of which hit the same address from neighbouring lanes today.
-# Changes the order of fp64 additions (still within the 1e-9 bar; the atomics' order is not fixed either).  Opt-in:
-# written after the round's GPU budget was spent, checked under emulation only.
-RUNAGG = os.environ.get("SDQLB200_RUNAGG", "0") == "1"
-# Tier 0 of a group-by (tiny key domain) with the thread-private accumulators in SHARED memory instead of registers: cell
-# (slot, field) of thread t lives at sm[(slot * nf + field) * kBlock + t] (conflict-free: consecutive lanes, consecutive
-# 8-byte words).  A row then updates only the nf cells of its slot (LDS + DADD + STS each) instead of running rcap x nf
-# predicated adds, and the kernel needs ~60 fewer registers: `q1_k0<0>` (the bench's dominant kernel) sits at 128
-# registers / 2 CTAs per SM / 16 warps per SM today with 32 % of its stall samples on long scoreboard.  Opt-in: written
-# after the round's GPU budget was spent, checked under emulation only.
-TIER0_SMEM = os.environ.get("SDQLB200_TIER0_SMEM", "0") == "1"
-# Early materialisation of the payload of build tables whose value expression itself contains lookups (a join chain:
-# Q9's partsupp entries carry the supplier's nation, found through two more tables): the fields consumers read are
-# evaluated ONCE, by the build kernel when it claims a slot, and stored in 8-byte arrays next to the slot; a consumer
-# then needs one load per field instead of re-walking the chain at the representative row (find + representative row +
-# gather per hop).  Opt-in: written after the round's GPU budget was spent, checked under emulation only (where the
-# counting build shows the data-dependent accesses drop, tests/test_stats.py).
-MATERIALISE = os.environ.get("SDQLB200_MATERIALISE", "0") == "1"
-# the insert side of PROBE32: keys of single-part tables over an int32 column are packed with 32-bit arithmetic in the
-# build / group-by kernels too (sdqlrt::pack_key1).  Opt-in, emulation-checked only.
-PACK32 = os.environ.get("SDQLB200_PACK32", "0") == "1"
+# queues); the host driver refuses relations of more than 2'000'000'000 rows.  B200 A/B on identical data
+# (profiles/r02_visit1/r02_ab_candidates_sf10.json, _sf100.log): Q5 -6 %, Q9 -6 %, Q10 -5 %, Q19 -7 %, Q20 -10 % at SF10, Q5
+# 3.98 -> 3.76 ms and Q10 5.22 -> 5.03 ms at SF100; Q17 +8 % at SF10 is the one regression.  SDQLB200_IDX32=0 restores
+# 64-bit indices (relations beyond 2^31 rows).
+IDX32 = os.environ.get("SDQLB200_IDX32", "1") == "1"
+# Tier 0 of a group-by (tiny key domain) keeps the thread-private accumulators in SHARED memory: cell (slot, field) of
+# thread t lives at sm[(slot * nf + field) * kBlock + t] (conflict-free: consecutive lanes, consecutive 8-byte words).  A
+# row updates only the nf cells of its slot (LDS + DADD + STS each) instead of running rcap x nf predicated adds, and the
+# kernel needs ~60 fewer registers -- which is what lets the scan loop double-buffer the next row group in registers
+# ("reg" pipeline).  B200 (profiles/r02_visit2): q1_k0 SF10 0.455 -> 0.373 ms (6.1 TB/s, 0.93 of the measured copy peak),
+# SF100 4.19 -> 3.42 ms (6.67 TB/s); with register accumulators the same loop needs 172 registers (1 CTA per SM).
+# SDQLB200_TIER0_SMEM=0 restores register accumulators.
+TIER0_SMEM = os.environ.get("SDQLB200_TIER0_SMEM", "1") == "1"
 
 
-def contains_lookup(e):
-    """does the IR expression contain a dictionary lookup?"""
-    if isinstance(e, ir.DicLookupExpr):
-        return True
-    if isinstance(e, ir.Expr):
-        return any(contains_lookup(x) for x in vars(e).values())
-    if isinstance(e, (list, tuple)):
-        return any(contains_lookup(x) for x in e)
-    return False
 COMPACT = os.environ.get("SDQLB200_COMPACT", "1") != "0"  # rows surviving a selective probe are queued and re-dealt to all lanes
 BITS_FILTER = os.environ.get("SDQLB200_BITS", "1") != "0"  # presence bitmaps in front of selective, probed tables
 COUNT_PASS = os.environ.get("SDQLB200_COUNT_PASS", "1") != "0"  # cardinality passes in front of selective table builds
@@ -233,8 +209,6 @@ class TableDesc:
         self.inner = None       # nested dict value: (n_outer_parts, [inner stats], inner key template SValue)
         self.probed = False     # looked up by some kernel (tbl_find): candidates for a presence filter
         self.distinct_of = None
-        self.mat = None         # early materialisation: OrderedDict field name (None = scalar value) -> (array index, leaf)
-        self.mat_names = None   # ... field names of the value record (None: the value is a single leaf)
 
     # -- element access ---------------------------------------------------------------------
     def src_elem(self, K, idx, prov=E):
@@ -288,31 +262,6 @@ class TableDesc:
             if self.scalar_value or self.count_only:
                 return vals[0][1]
             return SRec(vals)
-        if self.mat is not None:
-            # The value is evaluated symbolically in a scratch kernel (its code is thrown away) exactly as the late path
-            # would: the leaves carry the provenance / determination marks the functional-dependency minimisation of
-            # group keys needs (Q10 groups by seven fields of such a value).  Each leaf a consumer touches is then
-            # re-labelled to read the slot's array instead.
-            # one scratch kernel per consumer kernel: repeated lookups of the same entry (one per field access in the
-            # source) share their nested lookups -- and thereby their tokens -- through its CSE table, as they do on the
-            # late path through the consumer's own
-            Kd = K.__dict__.get("mat_scratch")
-            if Kd is None:
-                Kd = K.mat_scratch = Kernel(q, K.name + "_scratch", K.src)
-            keycode = None
-            if token is not None:
-                kv = flatten(Kd, self.key_fn(Kd, "0", prov))
-                if len(kv) == 1 and hasattr(kv[0], "code"):
-                    keycode = kv[0].code
-                elif len(kv) == 1 and kv[0].kind == "ref":
-                    keycode = ("ref", kv[0].arg, kv[0].col, kv[0].row)
-            v = mark(Kd, self.val_fn(Kd, "0", prov), prov, keycode, token)
-
-            def leaf(name):
-                return lambda: self.mat_leaf(name, sl, unwrap(v.field(Kd, name) if name is not None else v))
-            if self.mat_names is None:
-                return leaf(None)()
-            return SRec([(n, leaf(n)) for n in self.mat_names])
         rp = K.let("int", "sdqlrt::rep_of(c.%s, %s)" % (self.name, slot))
         keycode = None
         if token is not None:
@@ -323,45 +272,6 @@ class TableDesc:
                 keycode = ("ref", kv[0].arg, kv[0].col, kv[0].row)
         v = self.val_fn(K, rp, prov)
         return mark(K, v, prov, keycode, token)
-
-
-def _mat_template(v):
-    """kind of a materialised leaf, from a scratch evaluation of the value expression"""
-    v = unwrap(v)
-    if isinstance(v, SScalar):
-        return ("scalar", v.ctype, v.stats)
-    if isinstance(v, SStr) and v.kind == "ref":
-        return ("ref", v.arg, v.col, v.width)
-    if isinstance(v, SStr) and v.kind == "codeval":
-        return ("codeval", v.arg, v.col)
-    return None
-
-
-def _mat_leaf(self, name, sl, x):
-    """field ``name`` of the materialised value in slot ``sl``.  ``x`` = the leaf as the late path would compute it (from
-    a scratch evaluation): its marks are kept, its code is replaced by a load from the slot's array.  Registers the
-    field: the build kernel stores it (Query.splice_materialised)."""
-    tmpl = _mat_template(x)
-    if tmpl is None:
-        raise CodegenError("%s: field %r cannot be materialised" % (self.name, name))
-    if name not in self.mat:
-        j = len(self.fields)
-        self.fields.append((name, "f64" if (tmpl[0] == "scalar" and tmpl[1] == "f64") else "i64"))
-        self.mat[name] = (j, tmpl)
-    j, tmpl = self.mat[name]
-    code = "sdqlrt::ldg1(c.%s_a%d + %s)" % (self.name, j, sl)
-    if tmpl[0] == "scalar":
-        return SScalar(x.ctype, "(%s != 0)" % code if x.ctype == "bool" else code, x.prov, x.det, x.stats)
-    d = dict(x.__dict__)
-    kind = d.pop("kind")
-    if kind == "ref":
-        d["row"], d["scan"] = "(int)" + code, False
-    else:
-        d["code"] = "(int)" + code
-    return SStr(kind, **d)
-
-
-TableDesc.mat_leaf = _mat_leaf
 
 
 def leaf_kind(x):
@@ -640,6 +550,18 @@ class Kernel:
                 # compaction: the drain below must also run once after the last scan iteration (one copy of the body)
                 return ["    for (;;) {", "    const bool more_ = %s;" % cond, "    if (more_) {"]
 
+            def prefetches():
+                o = ["        { const %s gp = g + %d * gstride; if (gp < ngrp) {" % (IT, PF_DIST)]
+                for (col, rep), (arr, idx) in self.scan_cols.items():
+                    cg = self.count_guard(col, rep)
+                    for k in range(G):
+                        if rep == "code":
+                            o.append("            %ssdqlrt::prefetch_l2((const char*)c.in%d + %s((gp + %d * (%s)blockDim.x) << 2) * c.in%d_w);" % (cg, idx, "(long long)" if IDX32 else "", k, IT, idx))
+                        else:
+                            o.append("            %ssdqlrt::prefetch_l2(c.in%d + ((gp + %d * (%s)blockDim.x) << 2));" % (cg, idx, k, IT))
+                o.append("        } }")
+                return o
+
             pipe = self.pipe_mode() or "reg"
             if pipe == "reg":
                 for (col, rep), (arr, idx) in self.scan_cols.items():
@@ -657,15 +579,7 @@ class Kernel:
                 L += loop_head(loop_cond)
                 L.append("        const %s gn = g + gstride;" % IT)
                 L += stage
-                L.append("        { const %s gp = g + %d * gstride; if (gp < ngrp) {" % (IT, PF_DIST))
-                for (col, rep), (arr, idx) in self.scan_cols.items():
-                    cg = self.count_guard(col, rep)
-                    for k in range(G):
-                        if rep == "code":
-                            L.append("            %ssdqlrt::prefetch_l2((const char*)c.in%d + %s((gp + %d * (%s)blockDim.x) << 2) * c.in%d_w);" % (cg, idx, "(long long)" if IDX32 else "", k, IT, idx))
-                        else:
-                            L.append("            %ssdqlrt::prefetch_l2(c.in%d + ((gp + %d * (%s)blockDim.x) << 2));" % (cg, idx, k, IT))
-                L.append("        } }")
+                L += prefetches()
                 L += loads("r_", "g", "        ")
             L += ["        " + x for x in self.iter_pre]
             L.append("#pragma unroll")
@@ -974,9 +888,6 @@ class KeyedSink:
         K = self.K
         kk = K.tmp("kk")
         K.emit("unsigned long long %s = 0; bool %s_ok = true;" % (kk, kk))
-        if PACK32 and len(codes) == 1 and len(t.parts) == 1 and t.parts[0][0] == "col" and t.inner is None:
-            K.emit("%s_ok = sdqlrt::pack_key1((int)(%s), c.%s_mn[0], c.%s_rng[0], %s);" % (kk, codes[0], t.name, t.name, kk))
-            return kk
         for j, code in enumerate(codes):
             K.emit("%s_ok &= sdqlrt::pack_part(%s, c.%s_mn[%d], c.%s_rng[%d], c.%s_mul[%d], %s);" %
                    (kk, code, t.name, j, t.name, j, t.name, j, kk))
@@ -994,17 +905,7 @@ class BuildSink(KeyedSink):
         K, t = self.K, self.t
         self.count_open()
         kk = self.pack(t, self.setup_key(t, d.k))
-        if t.mat is not None:
-            # the slot's claimant stores the payload fields consumers ask for (filled in by Query.splice_materialised)
-            K.open_if("%s_ok" % kk)
-            K.emit("bool nw; const int slm_ = sdqlrt::tbl_upsert(c.%s, %s, (int)%s, nw);" % (t.name, kk, K.scan_var))
-            K.open_if("nw")
-            K.emit("/*MATERIALISE %s*/" % t.name)
-            t.mat_site = (K, K.depth, K.scan_var)
-            K.close()
-            K.close()
-        else:
-            K.emit("if (%s_ok) { bool nw; sdqlrt::tbl_upsert(c.%s, %s, (int)%s, nw); }" % (kk, t.name, kk, K.scan_var))
+        K.emit("if (%s_ok) { bool nw; sdqlrt::tbl_upsert(c.%s, %s, (int)%s, nw); }" % (kk, t.name, kk, K.scan_var))
         self.count_close()
 
     def finish(self):
@@ -1087,26 +988,9 @@ class GroupSink(KeyedSink):
             K.emit("    smrep[(int)%s] = (int)%s;" % (kk, K.scan_var))
             K.emit("} else {")
             K.depth += 1
-        if RUNAGG and K.src[0] == "rel" and K.scan_var == "i" and PIPELINE != "tma":
-            # run aggregation: this row either extends the thread's current run (same packed key) or closes it
-            cty = ["double" if ct == "f64" else "long long" for _, ct in t.fields]
-            flush = ["{ bool nw_; const int sl_ = sdqlrt::tbl_upsert(c.%s, rk_, rr_, nw_);" % t.name]
-            flush += ["  sdqlrt::red_add(c.%s_a%d + sl_, rv%d_);" % (t.name, j, j) for j in range(nf)]
-            flush.append("}")
-            if not getattr(K, "runagg", False):
-                K.runagg = True
-                K.iter_pre.append("unsigned long long rk_ = 0; int rr_ = 0; bool rp_ = false;  // the open run: key, first row, pending")
-                K.iter_pre.append(" ".join("%s rv%d_ = 0;" % (cty[j], j) for j in range(nf)))
-                K.iter_post.append("if (rp_) " + " ".join(flush))
-            K.emit("if (rp_ && %s == rk_) { %s }" % (kk, " ".join("rv%d_ += %s;" % (j, vals[j]) for j in range(nf))))
-            K.emit("else {")
-            K.emit("    if (rp_) " + " ".join(flush))
-            K.emit("    rk_ = %s; rr_ = (int)%s; rp_ = true; %s" % (kk, K.scan_var, " ".join("rv%d_ = %s;" % (j, vals[j]) for j in range(nf))))
-            K.emit("}")
-        else:
-            K.emit("bool nw; const int sl = sdqlrt::tbl_upsert(c.%s, %s, (int)%s, nw);" % (t.name, kk, K.scan_var))
-            for j in range(nf):
-                K.emit("sdqlrt::red_add(c.%s_a%d + sl, %s);" % (t.name, j, vals[j]))
+        K.emit("bool nw; const int sl = sdqlrt::tbl_upsert(c.%s, %s, (int)%s, nw);" % (t.name, kk, K.scan_var))
+        for j in range(nf):
+            K.emit("sdqlrt::red_add(c.%s_a%d + sl, %s);" % (t.name, j, vals[j]))
         if self.tiered:
             K.depth -= 1
             K.emit("}")
@@ -1481,40 +1365,6 @@ class Query:
             raise CodegenError("unsupported result value %s" % type(v).__name__)
         self.add_kernel(K)
 
-    def splice_materialised(self):
-        """early materialisation: now that every consumer has registered the payload fields it reads, the build kernels
-        get the code that evaluates those fields for the claiming row and stores them in the slot's arrays"""
-        for t in self.tables:
-            if t.mat is None or getattr(t, "mat_spliced", False):
-                continue
-            t.mat_spliced = True
-            K, depth, row = t.mat_site
-            marker = "/*MATERIALISE %s*/" % t.name
-            where = [(lst, i) for lst in (K.body, K.body2 or []) for i, x in enumerate(lst) if x.strip() == marker]
-            if not t.mat:
-                for lst, i in where:
-                    lst[i] = ""
-                continue
-            saved = (K.body, K.cse, K.depth, K.scan_var)
-            K.body, K.cse, K.depth, K.scan_var = [], [{}], depth, row
-            v = unwrap(t.val_fn(K, row))
-            for name, (j, tmpl) in t.mat.items():
-                x = unwrap(v.field(K, name) if name is not None else v)
-                if tmpl[0] == "scalar":
-                    code = x.code if tmpl[1] != "f64" else "__double_as_longlong(%s)" % x.code
-                    if tmpl[1] == "f64":
-                        K.emit("c.%s_a%d[slm_] = %s;" % (t.name, j, x.code))
-                    else:
-                        K.emit("c.%s_a%d[slm_] = (long long)(%s);" % (t.name, j, code))
-                elif tmpl[0] == "ref":
-                    K.emit("c.%s_a%d[slm_] = (long long)(%s);" % (t.name, j, x.row if not x.scan else row))
-                else:
-                    K.emit("c.%s_a%d[slm_] = (long long)(%s);" % (t.name, j, self.str_code(K, x)))
-            code = K.body
-            K.body, K.cse, K.depth, K.scan_var = saved
-            for lst, i in where:
-                lst[i:i + 1] = code
-
     def materialise_table(self, t):
         K = Kernel(self, "%s_fin" % self.name, ("tbl", t))
         elem = SPair(t.key_at(K, "i"), t.value_at(K, "i", None))
@@ -1641,7 +1491,7 @@ class Query:
         if K.sink is None:
             K.sink = self.make_sink(K, v)
             if isinstance(K.sink, (BuildSink, GroupSink)):
-                self.bind_table_fns(K, K.sink.t, e, env, allow_mat=isinstance(K.sink, BuildSink))
+                self.bind_table_fns(K, K.sink.t, e, env)
                 if K.depth > 0 and K.src[0] in ("rel", "tbl") and COUNT_PASS:
                     K.enable_count()
         K.sink.produce(v)
@@ -1651,7 +1501,7 @@ class Query:
                 if sub is not None and sub.t.key_fn is None:
                     self.bind_table_fns(K, sub.t, fe, env)
 
-    def bind_table_fns(self, K, t, e, env, allow_mat=False):
+    def bind_table_fns(self, K, t, e, env):
         """closures that re-evaluate the key / value expression of a produced {k: v} at a given source index."""
         S = K.S
         q = self
@@ -1677,21 +1527,6 @@ class Query:
             return q.ev(vexpr, env2, K2)
 
         t.key_fn, t.val_fn = key_fn, val_fn
-        if MATERIALISE and allow_mat and K.src[0] == "rel" and PIPELINE != "tma" and contains_lookup(vexpr):
-            # shape and leaf kinds of the value from a scratch evaluation (its code is thrown away)
-            Kd = Kernel(q, K.name + "_scratch", K.src)
-            Kd.S, Kd.root_env, Kd.row_var = K.S, K.root_env, K.row_var
-            try:
-                v = unwrap(val_fn(Kd, "0"))
-            except CodegenError:
-                return
-            if isinstance(v, (SRec, SRow)):
-                items = v.items(Kd)
-                names, tmpls = [n for n, _ in items], {n: _mat_template(x) for n, x in items}
-            else:
-                names, tmpls = None, {None: _mat_template(v)}
-            if any(x is not None for x in tmpls.values()):
-                t.mat, t.mat_names, t.mat_templates = OrderedDict(), names, tmpls
 
     def nested_sum(self, S, env, K):
         d = self.ev(S.dictExpr, env, K)
@@ -2149,7 +1984,6 @@ def render_query(q):
         L.append("    long long* res%d;" % j)
     L.append("};")
     L.append("")
-    q.splice_materialised()
     for K in q.kernels:
         L.append(K.render())
         L.append("")

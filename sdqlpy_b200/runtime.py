@@ -325,13 +325,32 @@ def host_strings(src, rows):
 # ---------------------------------------------------------------------------------------------
 # results (fastd-compatible surface)
 # ---------------------------------------------------------------------------------------------
+def _key_values(rec):
+    """field values of a ``record`` (this package's or the reference's: both keep an ordered dict behind
+    getContainer(); the reference's C code reads the same dict through ``_sr_dict__container``, fdg:247, 273)"""
+    if hasattr(rec, "getContainer"):
+        return tuple(rec.getContainer().values())
+    if isinstance(rec, dict):
+        return tuple(rec.values())
+    return tuple(rec)
+
+
 class ResultSet:
-    """set of records returned by a query: the surface of the reference's fastd wrapper (fastd.py:31-51).
-    Like the reference's FastDict it stays in native (columnar) form; Python tuples / records are only built when
-    asked for (tuples(), to_dict(), print), with string fields gathered from the host columns by row id."""
+    """set of records returned by a query: the surface of the reference's fastd wrapper (fastd.py:31-51) over its
+    generated ``FastDict_<abbr>_b`` type (fast_dict_generator.py:241-342) -- ``size / print / to_dict / get / set /
+    from_dict``.  Like the reference's FastDict it stays in native (columnar) form; Python tuples / records are only
+    built when asked for, with string fields gathered from the host columns by row id.
+
+    Reference behaviours kept: ``set(key, value)`` stores ``true`` whatever ``value`` is (fdg:264) and returns True;
+    ``get(key)`` is ``dict[key] == true`` and therefore INSERTS a missing key with ``false`` (fdg:289, phmap
+    ``operator[]``) -- ``size()`` grows and ``print()`` shows ``<..> -> false``; ``to_dict()`` maps every stored key to
+    True (fdg:338).  Deviation: string fields are returned without the NUL padding of ``VarChar<n>``."""
+
+    types = None  # (record, sr_dict) classes to_dict() builds; None = this package's
 
     def __init__(self, names, rows=None, lazy=None):
         self.names, self._rows, self._lazy = list(names), rows, lazy
+        self._flags = None  # row tuple -> bool, only once get / set / from_dict touched the set
 
     @property
     def rows(self):
@@ -342,7 +361,14 @@ class ResultSet:
             self._lazy = None
         return self._rows
 
+    def _map(self):
+        if self._flags is None:
+            self._flags = dict.fromkeys(self.rows, True)
+        return self._flags
+
     def size(self):
+        if self._flags is not None:
+            return len(self._flags)
         if self._rows is None:
             cols, _ = self._lazy
             return int(len(cols[0])) if cols else 0
@@ -350,20 +376,56 @@ class ResultSet:
 
     __len__ = size
 
+    def set(self, key, value=True):
+        m = self._map()
+        k = _key_values(key)
+        if k not in m:
+            self._rows.append(k)
+        m[k] = True
+        return True
+
+    def get(self, key):
+        m = self._map()
+        k = _key_values(key)
+        if k not in m:
+            self._rows.append(k)
+            m[k] = False
+        return m[k]
+
+    def from_dict(self, data_dict):
+        if hasattr(data_dict, "getContainer"):
+            data_dict = data_dict.getContainer()
+        for k, v in data_dict.items():
+            self.set(k, v)
+        return True
+
     def to_dict(self):
-        from .sdql_lib import record, sr_dict
+        if self.types is not None:
+            record, sr_dict = self.types
+        else:
+            from .sdql_lib import record, sr_dict
         return sr_dict({record(dict(zip(self.names, r))): True for r in self.rows})
 
     def tuples(self):
         return list(self.rows)
 
-    def __str__(self):  # 2-decimal printing like the reference (phmap.h:83)
+    def __str__(self):
+        """the text ``cout << dict`` prints (phmap.h:78-93, tuple_helper.h:21-34): fixed 2-decimal floats, boolalpha"""
         def f(v):
+            if isinstance(v, bool):
+                return "true" if v else "false"
             return "%.2f" % v if isinstance(v, float) else str(v)
-        return "{" + ", ".join("<" + ",".join(f(v) for v in r) + ">:true" for r in self.rows) + "}"
+        flags = self._flags
+        return "{ " + ", ".join("<" + ",".join(f(v) for v in r) + "> -> " + ("true" if flags is None or flags[r] else "false")
+                                 for r in self.rows) + " }"
 
     def print(self):
         print(str(self))
+
+
+class fastd(ResultSet):
+    """the class name the reference's ``benchmark()`` looks for (``res.__class__.__name__ == "fastd"``, lib:457-470):
+    results handed out through the importable ``<script>_compiled`` stub are of this type"""
 
 
 # ---------------------------------------------------------------------------------------------
@@ -633,6 +695,26 @@ class CompiledModule:
             else:
                 raise ValueError(fk)
         return ResultSet(names, None, (cols, decoders))
+
+
+def stub_entry(mod, name):
+    """``<fn>_compiled(db)`` as exported by the importable ``<script>_compiled`` stub (build.write_stub): results are
+    ``fastd`` objects; when the caller runs under the reference's own package, ``to_dict()`` builds the reference's
+    ``record`` / ``sr_dict`` (its C code imports the top-level ``sdql_lib`` for them, fast_dict_generator.py:315-316)."""
+    import sys
+
+    def call(db):
+        res = mod.run(name, db)
+        if isinstance(res, ResultSet):
+            res.__class__ = fastd
+            for m in ("sdqlpy.sdql_lib", "sdql_lib"):
+                lib = sys.modules.get(m)
+                if lib is not None and hasattr(lib, "record") and hasattr(lib, "sr_dict"):
+                    res.types = (lib.record, lib.sr_dict)
+                    break
+        return res
+    call.__name__ = name + "_compiled"
+    return call
 
 
 _modules = {}

@@ -119,11 +119,9 @@ def test_ragged_relations_match_reference(emu_module, q):
     assert compare(got, golden("ragged")[q]) is None
 
 
-def test_opt_in_code_generator_switches_keep_results(tmp_path):
-    """switches that are off by default (SDQLB200_IDX32: 32-bit row indices, SDQLB200_RUNAGG: run aggregation in front of
-    the global-tier atomics, SDQLB200_TIER0_SMEM: thread-private tier-0 accumulators in shared memory, SDQLB200_MATERIALISE: payloads of
-    join-chain build tables stored next to the slot) or that have an A/B partner build
-    (PROBE32 / RECONVERGE / TEXTSCAN off): the generated module must still reproduce the reference's outputs.  The code
+def test_code_generator_switches_keep_results(tmp_path):
+    """the A/B partner builds of the defaults (64-bit row indices, register tier-0 accumulators, L2-prefetch pipeline,
+    PROBE32 / RECONVERGE / TEXTSCAN off) must reproduce the reference's outputs like the default build.  The code
     generator reads its switches at import, hence the subprocess."""
     import subprocess
     import sys
@@ -146,7 +144,8 @@ for q in qs:
     assert d is None, (q, d)
 print("ok")
 ''' % {"root": os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tmp": str(tmp_path)}
-    for tag, env in (("idx32", {"SDQLB200_IDX32": "1"}), ("runagg", {"SDQLB200_RUNAGG": "1"}), ("tier0smem", {"SDQLB200_TIER0_SMEM": "1"}), ("mat", {"SDQLB200_MATERIALISE": "1"}), ("pack32", {"SDQLB200_PACK32": "1"}),
+    for tag, env in (("idx64", {"SDQLB200_IDX32": "0"}), ("tier0reg", {"SDQLB200_TIER0_SMEM": "0", "SDQLB200_PIPELINE": "l2"}),
+                     ("allreg", {"SDQLB200_PIPELINE": "reg"}),
                      ("plain", {"SDQLB200_PROBE32": "0", "SDQLB200_RECONVERGE": "0", "SDQLB200_TEXTSCAN": "0"})):
         e = dict(os.environ, TAG=tag, **env)
         r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=e)
