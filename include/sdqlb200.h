@@ -30,6 +30,8 @@ enum { SDQLB200_SUM_F64 = 0, SDQLB200_SUM_I64 = 1, SDQLB200_MIN_I32 = 2, SDQLB20
  * destination, all-gather, write back).  The reference's counterpart is the serial AddMap merge of thread-local
  * phmap tables (map_helper.h:2-23, sdql_ir_cpp_generator_par.py:436-438). */
 typedef int (*sdqlb200_merge_fn)(void* ctx, uint64_t workspace_offset, uint64_t count, int32_t op);
+/* The product implementation is sdqlb200_comm_merge of include/sdqlb200_comm.h (NVLink peer-memory all-reduce for small
+ * partials, NCCL for large ones, hash all-to-all for hashed tables; plain C, no host synchronisation for SUM / MIN). */
 
 /* one hashed device dictionary: open addressing, linear probing, keys[slot] == ~0 means free */
 typedef struct {
@@ -84,6 +86,9 @@ typedef struct {
     int32_t result_partial;   /* out: 1 = result rows are this rank's share (concatenate ranks) */
     int32_t rank;             /* this process' rank among the GPUs (0 on a single GPU)          */
     int32_t world;            /* number of ranks (0 or 1 on a single GPU)                       */
+    const int64_t* nrows_global; /* multi-GPU: rows of each relation argument over ALL ranks (NULL on a single GPU).
+                               * Tables that are merged across ranks are planned (direct vs hashed, slots) from these, so
+                               * every rank takes the same decisions and a hashed table holds the union of the ranks' keys */
 } sdqlb200_args;
 
 int sdqlb200_num_queries(void);

@@ -47,6 +47,7 @@ class _SplitDone(Exception):
 #   "l2"  = 128-bit LDGs, single register buffer plus prefetch.global.L2 of the group PF_DIST iterations ahead
 PIPELINE = os.environ.get("SDQLB200_PIPELINE", "auto")  # auto | tma | reg | l2 (see Kernel.pipe_mode)
 PF_DIST = int(os.environ.get("SDQLB200_PF_DIST", "2"))
+AUTO_PIPE = os.environ.get("SDQLB200_AUTO_PIPE", "reg")  # what "auto" picks for tiered (group-by) kernels
 RING_ROWS_PER_THREAD = int(os.environ.get("SDQLB200_RING_ROWS", "0"))  # 0 = per kernel (Kernel.ring_rows)
 RING_MAX_ROW_BYTES = 100     # wider scans cannot keep two stages in 227 KB of shared memory: they use LDGs
 # string columns of the scanned row staged through shared memory: measured on B200 (SF10) Q13 2.25 ms staged vs 1.80 ms
@@ -265,6 +266,9 @@ class TableDesc:
         rp = K.let("int", "sdqlrt::rep_of(c.%s, %s)" % (self.name, slot))
         keycode = None
         if token is not None:
+            # a probe reads this entry's payload through its representative source row: only valid where that row is
+            # local (after a cross-GPU merge the entries of other ranks have no local representative, merge_code)
+            self.rep_probed = True
             kv = flatten(K, self.key_fn(K, rp, prov))
             if len(kv) == 1 and hasattr(kv[0], "code"):
                 keycode = kv[0].code
@@ -401,9 +405,14 @@ class Kernel:
             return None
         pipe = PIPELINE
         if pipe == "auto":
-            # measured on B200 at SF10 (profiles/r01_pipeline_ab.json): the LDG pipelines beat the TMA ring on every
-            # kernel class (Q1 0.43 vs 0.51 ms, Q6 0.236 vs 0.243 ms, Q18 pass 1 0.35 vs 0.45 ms), so the ring is opt-in
-            pipe = "l2" if (self.tiered or len(self.scan_cols) >= 6) else "reg"
+            # measured on B200 (profiles/r01_pipeline_ab.json, profiles/r02_visit2): the LDG pipelines beat the TMA ring on
+            # every kernel class.  Group-by kernels keep their tier-0 accumulators in shared memory, so they can afford the
+            # register double buffer (q1_k0: 120 registers, 2 CTAs per SM, 6.1-6.7 TB/s against 5.2 TB/s with the L2-prefetch
+            # loop); wide scans without a tier use the single buffer + L2 prefetch.  SDQLB200_AUTO_PIPE=l2: the round-1 rule.
+            if AUTO_PIPE == "l2":
+                pipe = "l2" if (self.tiered or len(self.scan_cols) >= 6) else "reg"
+            else:
+                pipe = "l2" if (not self.tiered and len(self.scan_cols) >= 6) else "reg"
         if pipe == "tma" and sum({"i32": 4, "f64": 8, "code": 4}[rep] for (_, rep) in self.scan_cols) > RING_MAX_ROW_BYTES:
             pipe = "l2"
         return pipe
@@ -1904,6 +1913,11 @@ def merge_code(q, K):
         cop = " || ".join("((a->cols[%d].flags & SDQLB200_COL_PARTKEY) != 0)" % p[1] for p in t.parts if p[0] == "col") or "false"
         L.append("        part_%s = true;  // iteration over this table is partitioned (by key range or by owner rank)" % t.name)
         L.append("        if (!(%s)) {" % cop)
+        if t.kind == "build" and getattr(t, "rep_probed", False):
+            # the payload of such an entry is re-evaluated at its representative source row, which only the owner rank
+            # holds: a probe on another rank would read row 0 of its own partition instead (silently wrong)
+            L.append("            return sdqlhost::fail(SDQLB200_E_ARG, \"%s: table %s is built from a partitioned relation, keyed by a column the relation "
+                     "is not partitioned on, and probed for its payload: replicate the relation or partition it on that key\");" % (q.name, t.name))
         L.append("            if (!c.%s.direct) {  // hashed partial dictionary: hash all-to-all + combine + all-gather (SDQLB200_MERGE_TABLE)" % t.name)
         L.append("                sdqlb200_table td; memset(&td, 0, sizeof td);")
         L.append("                td.keys = (uint64_t*)c.%s.keys; td.rep = c.%s.rep; td.cap = c.%s.cap; td.nfields = %d; td.f64_mask = %du;" %
@@ -2022,6 +2036,14 @@ def render_query(q):
         src = "c.n_%s" % t.src[1] if t.src[0] == "rel" else "c.%s.cap" % t.src[1].name
         nf = len(t.fields)
         L.append("    {")
+        if t.src[0] == "rel":
+            # a table that will be merged across ranks is planned from the relation's GLOBAL row count: all ranks agree on
+            # direct vs hashed and on the slots, and a hashed table has room for the union of the ranks' keys
+            ai = q.args.index(t.src[1])
+            cop = " || ".join("((a->cols[%d].flags & SDQLB200_COL_PARTKEY) != 0)" % p_[1] for p_ in t.parts if p_[0] == "col") or "false"
+            L.append("        const long long rows_ = (a->merge && a->nrows_global && ((a->part_mask >> %d) & 1u) && !(%s)) ? (long long)a->nrows_global[%d] : c.n_%s;" %
+                     (ai, cop, ai, t.src[1]))
+            src = "rows_"
         L.append("        long long mn[%d] = {%s}, rng[%d] = {%s};" % (P, mns, P, rgs))
         L.append("        void* ag[%d] = {nullptr};" % max(1, nf))
         # presence bits in front of tables that are probed and built selectively (predicates in front of the build)
@@ -2198,16 +2220,17 @@ def render_query(q):
             L.append("    SDQL_LAUNCH(%s, g_%s, sdqlrt::kBlock, sm_%s, st, c);" % (K.name, K.name, K.name))
         L.append("    SDQL_CUDA(cudaGetLastError()); ++launches;")
         L.append("    sdqlhost_step(st, \"%s\");" % K.name)
-        mc = merge_code(q, K)
-        L += mc
-        if mc:
-            L.append("    sdqlhost_step(st, \"%s:merge\");" % K.name)
-        for t in bits_tabs:  # presence bits of the finished table (one pass over its slots)
+        for t in bits_tabs:  # presence bits of the finished table (one pass over its slots; never for merged tables)
             L.append("    if (c.%s.bits) { SDQL_LAUNCH(sdqlrt::k_tbl_bits, sdqlhost::grid_for(c.%s.cap, 8, sms), sdqlrt::kBlock, 0, st, c.%s); SDQL_CUDA(cudaGetLastError()); }" %
                      (t.name, t.name, t.name))
         if bits_tabs:
             L.append("    sdqlhost_step(st, \"%s:bits\");" % K.name)
+        # the kernel's own time ends here: the cross-GPU merge that follows is charged to the next interval
         L.append("    if (kt && launches < 24) SDQL_CUDA(cudaEventRecord(sdqlhost_kev(launches), st));")
+        mc = merge_code(q, K)
+        L += mc
+        if mc:
+            L.append("    sdqlhost_step(st, \"%s:merge\");" % K.name)
     L.append("    SDQL_CUDA(cudaEventRecord(sdqlhost_ev(1), st));")
     L.append("    a->launches = launches;")
     L.append("    a->result_partial = %s ? 1 : 0;" % part_expr(q.kernels[-1]))
@@ -2238,14 +2261,15 @@ MODULE_HEAD = r'''// GENERATED by sdqlpy_b200.codegen -- do not edit.  Source wo
 #include "sdqlb200_host.h"
 
 #ifndef SDQLB200_EMU
-static cudaEvent_t g_ev[2];
-static bool g_ev_init = false;
+// per host thread: one thread drives one GPU (events, occupancy results and staging buffers belong to its device)
+static thread_local cudaEvent_t g_ev[2];
+static thread_local bool g_ev_init = false;
 static cudaEvent_t sdqlhost_ev(int i) {
     if (!g_ev_init) { cudaEventCreate(&g_ev[0]); cudaEventCreate(&g_ev[1]); g_ev_init = true; }
     return g_ev[i];
 }
-static cudaEvent_t g_kev[25];
-static bool g_kev_init = false;
+static thread_local cudaEvent_t g_kev[25];
+static thread_local bool g_kev_init = false;
 static cudaEvent_t sdqlhost_kev(int i) {
     if (!g_kev_init) { for (int k = 0; k < 25; ++k) cudaEventCreate(&g_kev[k]); g_kev_init = true; }
     return g_kev[i];
@@ -2254,8 +2278,8 @@ static cudaEvent_t sdqlhost_kev(int i) {
 // memory limit); cached per (kernel, size) so steady-state launches make no driver queries
 static int sdqlhost_occupancy(const void* fn, size_t smem) {
     struct Ent { const void* fn; size_t smem; int nb; };
-    static Ent cache[512];
-    static int used = 0;
+    static thread_local Ent cache[512];
+    static thread_local int used = 0;
     for (int i = 0; i < used; ++i)
         if (cache[i].fn == fn && cache[i].smem == smem) return cache[i].nb;
     int nb = 0;
@@ -2274,10 +2298,10 @@ static int sdqlhost_sms() {
 // SDQLB200_F_TRACE (or SDQLB200_DEBUG=1): wall-clock time of every step of the host driver on stderr (the stream is
 // drained after each step, so the figures are per step and the query as a whole runs slower than normal).
 // what == nullptr restarts the clock.
-static bool g_trace = false;
+static thread_local bool g_trace = false;
 static void sdqlhost_step(cudaStream_t st, const char* what) {
     if (!g_trace) return;
-    static double last = 0;
+    static thread_local double last = 0;
     cudaStreamSynchronize(st);
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -2286,7 +2310,7 @@ static void sdqlhost_step(cudaStream_t st, const char* what) {
     last = now;
 }
 
-static unsigned long long g_init_bytes = 0;  // bytes of table arrays initialised since the last sdqlb200_stats() call
+static thread_local unsigned long long g_init_bytes = 0;  // bytes of table arrays initialised since the last sdqlb200_stats() call
 // fill a dictionary's key / representative arrays with 0xFF (free) and zero its aggregate arrays
 static cudaError_t sdqlhost_init_table(void* ws, const sdqlhost::TblRegion& r, cudaStream_t st) {
     g_init_bytes += r.ff_len + r.z_len;
@@ -2302,7 +2326,7 @@ static int sdqlhost_fetch(sdqlb200_args* a, cudaStream_t st, unsigned long long*
                           long long* const* d_cols) {
     unsigned long long cnt = 0;
     const size_t span = nf ? (size_t)((char*)(d_cols[nf - 1] + cap) - (char*)d_count) : 8;
-    static char* stage = nullptr;
+    static thread_local char* stage = nullptr;  // per thread: concurrent sdqlb200_run calls do not share it
     const size_t kStage = 1 << 20;
 #ifndef SDQLB200_EMU
     if (!stage && cudaHostAlloc((void**)&stage, kStage, cudaHostAllocDefault) != cudaSuccess) stage = nullptr;

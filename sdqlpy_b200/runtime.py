@@ -13,6 +13,7 @@ without the built module) every entry point raises.
 import ctypes
 import json
 import os
+import threading
 
 import numpy as np
 
@@ -44,7 +45,7 @@ class Args(ctypes.Structure):
                 ("tier", ctypes.c_int32), ("reserved", ctypes.c_int32), ("result", Result),
                 ("kernel_ms", ctypes.c_float * 24), ("merge", ctypes.c_void_p), ("merge_ctx", ctypes.c_void_p),
                 ("part_mask", ctypes.c_uint32), ("result_partial", ctypes.c_int32), ("rank", ctypes.c_int32),
-                ("world", ctypes.c_int32)]
+                ("world", ctypes.c_int32), ("nrows_global", ctypes.POINTER(ctypes.c_int64))]
 
 
 class Table(ctypes.Structure):  # == sdqlb200_table
@@ -135,11 +136,22 @@ class CudaBackend:
         self.torch.cuda.synchronize()
 
 
+class _Context(threading.local):
+    """per host thread: sdqlpy_init(mode, N > 1) drives N GPUs from N threads of ONE process (Engine below); each of them
+    has its own device back end, column store and rank.  None = the process-wide defaults."""
+    backend = None
+    store = None
+    dist = None
+
+
+_ctx = _Context()
 _backend = None
 
 
 def backend():
     global _backend
+    if _ctx.backend is not None:
+        return _ctx.backend
     if _backend is None:
         _backend = CudaBackend()
     return _backend
@@ -276,32 +288,173 @@ class ColumnStore:
         self.cache.clear()
 
 
-STORE = ColumnStore()
+_STORE = ColumnStore()
+
+
+class _StoreProxy:
+    """``runtime.STORE``: the calling thread's column store (one per GPU under Engine, else the process-wide one)"""
+
+    def _cur(self):
+        return _ctx.store if _ctx.store is not None else _STORE
+
+    def __getattr__(self, name):
+        return getattr(self._cur(), name)
+
+    def __setattr__(self, name, value):
+        setattr(self._cur(), name, value)
+
+
+STORE = _StoreProxy()
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-GPU: the exchange library (include/sdqlb200_comm.h) and who is which rank
+# ---------------------------------------------------------------------------------------------
+class CommCtx(ctypes.Structure):  # == sdqlb200_comm_ctx
+    _fields_ = [("comm", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("stream", ctypes.c_void_p),
+                ("merges", ctypes.c_int64), ("table_merges", ctypes.c_int64), ("p2p_merges", ctypes.c_int64)]
+
+
+_comm_lib = None
+
+
+def comm_lib():
+    """libsdqlb200_comm.so through ctypes (built by build.compile_comm / __graft_entry__.build)."""
+    global _comm_lib
+    if _comm_lib is None:
+        so = os.path.join(build.PKG, "_build", "libsdqlb200_comm.so")
+        if not os.path.exists(so):
+            raise ImportError("%s not found (run __graft_entry__.build())" % so)
+        L = ctypes.CDLL(so)
+        vp, i32, i64, u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64
+        L.sdqlb200_comm_last_error.restype = ctypes.c_char_p
+        L.sdqlb200_comm_unique_id.argtypes = [vp]
+        L.sdqlb200_comm_create.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
+        L.sdqlb200_comm_ipc_handle.argtypes = [vp, vp]
+        L.sdqlb200_comm_open_peers.argtypes = [vp, vp]
+        L.sdqlb200_comm_create_all.argtypes = [i32, ctypes.POINTER(i32), ctypes.POINTER(vp)]
+        L.sdqlb200_comm_destroy.argtypes = [vp]
+        L.sdqlb200_comm_p2p.argtypes = [vp]
+        L.sdqlb200_comm_allreduce.argtypes = [vp, vp, u64, i32, vp]
+        L.sdqlb200_comm_host_max.argtypes = [vp, ctypes.POINTER(i64), i32, vp]
+        L.sdqlb200_comm_barrier.argtypes = [vp, vp]
+        L.sdqlb200_comm_gather_rows.argtypes = [vp, ctypes.POINTER(ctypes.POINTER(i64)), i32, i64,
+                                                ctypes.POINTER(ctypes.POINTER(i64)), ctypes.POINTER(i64), vp]
+        L.sdqlb200_comm_merge_table.argtypes = [vp, vp, vp]
+        _comm_lib = L
+    return _comm_lib
+
+
+def _comm_check(rc, what):
+    if rc < 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, comm_lib().sdqlb200_comm_last_error().decode()))
+    return rc
 
 
 class DistConfig:
-    """multi-GPU execution (one process per GPU, torch.distributed): which relation arguments are range
-    partitioned across ranks and which columns they are partitioned on."""
+    """multi-GPU execution: which relation arguments are range partitioned across the ranks and which columns they are
+    partitioned on, plus the rank's communicator.
 
-    def __init__(self, partitioned=("li", "ord"), partkeys=("l_orderkey", "o_orderkey"), group=None):
+    One process per GPU (torchrun): ``torch.distributed`` is the plumbing -- it carries the NCCL id and the IPC handles of
+    the peer-memory mailboxes at start-up (``connect()``); from then on every merge is the plain C function
+    ``sdqlb200_comm_merge`` called by the generated module itself.  Under gloo (the CPU tests) there is no communicator
+    and the merges go through the Python callback ``CompiledModule._merge`` instead."""
+
+    def __init__(self, partitioned=("li", "ord"), partkeys=("l_orderkey", "o_orderkey"), group=None, comm=None):
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.partitioned, self.partkeys = set(partitioned), set(partkeys)
         self.stats = {}
+        self.comm = comm   # sdqlb200_comm* (c_void_p) or None
+        self.p2p = False
+        if comm is None and self.world > 1 and dist.get_backend(group) == "nccl":
+            self.connect()
+
+    def connect(self):
+        """create this rank's communicator and map the peers' mailboxes"""
+        import torch
+        L, d = comm_lib(), self.dist
+        ident = ctypes.create_string_buffer(128)
+        if self.rank == 0:
+            _comm_check(L.sdqlb200_comm_unique_id(ident), "comm_unique_id")
+        box = [ident.raw]
+        d.broadcast_object_list(box, src=0, group=self.group)
+        h = ctypes.c_void_p()
+        _comm_check(L.sdqlb200_comm_create(ctypes.c_char_p(box[0]), self.rank, self.world, ctypes.byref(h)), "comm_create")
+        self.comm = h
+        mine = ctypes.create_string_buffer(64)
+        ok = L.sdqlb200_comm_ipc_handle(h, mine) == 0
+        handles = [None] * self.world
+        d.all_gather_object(handles, mine.raw if ok else None, group=self.group)
+        if all(x is not None for x in handles) and os.environ.get("SDQLB200_P2P", "1") != "0":
+            rc = L.sdqlb200_comm_open_peers(h, ctypes.c_char_p(b"".join(handles)))
+            flags = [None] * self.world
+            d.all_gather_object(flags, rc == 0, group=self.group)
+            self.p2p = all(flags)
+            if not self.p2p:  # one rank could not map a peer: every rank must take the NCCL path (they have to agree)
+                raise RuntimeError("peer-memory mailboxes could not be mapped on every rank (%r); set SDQLB200_P2P=0" % (flags,))
+        torch.cuda.synchronize()
+
+    def host_max(self, values):
+        """element-wise max over the ranks of a few Python ints (start-up / first call of a query only)"""
+        import torch
+        if self.comm is not None:
+            arr = (ctypes.c_int64 * len(values))(*values)
+            _comm_check(comm_lib().sdqlb200_comm_host_max(self.comm, arr, len(values), backend().stream()), "comm_host_max")
+            return [int(x) for x in arr]
+        t = torch.tensor(list(values), dtype=torch.int64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return [int(x) for x in t]
 
     def global_range(self, key, mn, mx):
         """column statistics must agree on all ranks: merged tables use them as packing radices."""
-        import torch
         if key not in self.stats:
-            dev = "cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu"
-            t = torch.tensor([-mn, mx], dtype=torch.int64, device=dev)
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
-            self.stats[key] = (-int(t[0]), int(t[1]))
+            a, b = self.host_max([-mn, mx])
+            self.stats[key] = (-a, b)
         return self.stats[key]
+
+    def global_rows(self, key, rows):
+        """rows of a partitioned relation over all ranks, as max over ranks x world: a rank-independent bound from which
+        merged tables are planned (sdqlb200_args.nrows_global)"""
+        k = ("rows",) + tuple(key)
+        if k not in self.stats:
+            self.stats[k] = self.host_max([rows])[0] * self.world
+        return self.stats[k]
+
+    def gather_rows(self, cols):
+        """concatenation of the ranks' result columns (lists of int64 numpy arrays) in rank order, on every rank"""
+        nf = len(cols)
+        n = len(cols[0]) if nf else 0
+        if self.comm is not None:
+            L = comm_lib()
+            P64 = ctypes.POINTER(ctypes.c_int64)
+            keep = [np.ascontiguousarray(c, dtype=np.int64) for c in cols]
+            src = (P64 * max(1, nf))(*[k.ctypes.data_as(P64) for k in keep])
+            out = (P64 * max(1, nf))()
+            total = ctypes.c_int64()
+            _comm_check(L.sdqlb200_comm_gather_rows(self.comm, src, nf, n, out, ctypes.byref(total), backend().stream()), "comm_gather_rows")
+            res = []
+            libc = ctypes.CDLL(None)
+            libc.free.argtypes = [ctypes.c_void_p]
+            for j in range(nf):
+                if total.value:
+                    res.append(np.ctypeslib.as_array(out[j], shape=(total.value,)).copy())
+                    libc.free(ctypes.cast(out[j], ctypes.c_void_p))
+                else:
+                    res.append(np.zeros(0, dtype=np.int64))
+            return res
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, cols, group=self.group)
+        return [np.concatenate([p_[j] for p_ in parts]) for j in range(nf)]
 
 
 DIST = None
+
+
+def dist_config():
+    """the calling thread's rank configuration (None on a single GPU)"""
+    return _ctx.dist if _ctx.dist is not None else DIST
 
 
 def set_distributed(cfg):
@@ -451,12 +604,45 @@ class CompiledModule:
         self.lib.sdqlb200_table_absorb.argtypes = [ctypes.POINTER(Table), vp, i64, i32, i32, vp, vp]
         man = json.loads(self.lib.sdqlb200_manifest().decode())
         self.queries = {q["name"]: q for q in man["queries"]}
-        self.ws = None
-        self.ws_bytes = 0
-        self.last = None
-        self._merge_cb, self.merges, self.merge_error = None, 0, None
+        self._tl = threading.local()  # workspace, last run, merge state: per host thread (= per GPU under Engine)
         for name in self.queries:
             setattr(self, name + "_compiled", self._make(name))
+
+    def _state(self):
+        t = self._tl
+        if not hasattr(t, "ws"):
+            t.ws, t.ws_bytes, t.last = None, 0, None
+            t.merge_cb, t.merges, t.table_merges, t.merge_error, t.comm_ctx = None, 0, 0, None, None
+        return t
+
+    # the per-thread state under its historical attribute names
+    ws = property(lambda self: self._state().ws, lambda self, v: setattr(self._state(), "ws", v))
+    ws_bytes = property(lambda self: self._state().ws_bytes, lambda self, v: setattr(self._state(), "ws_bytes", v))
+    last = property(lambda self: self._state().last, lambda self, v: setattr(self._state(), "last", v))
+    merge_error = property(lambda self: self._state().merge_error, lambda self, v: setattr(self._state(), "merge_error", v))
+
+    @property
+    def merges(self):
+        st = self._state()
+        return st.merges + (int(st.comm_ctx.merges) if st.comm_ctx is not None else 0)
+
+    @merges.setter
+    def merges(self, v):
+        self._state().merges = v
+
+    @property
+    def table_merges(self):
+        st = self._state()
+        return st.table_merges + (int(st.comm_ctx.table_merges) if st.comm_ctx is not None else 0)
+
+    @table_merges.setter
+    def table_merges(self, v):
+        self._state().table_merges = v
+
+    @property
+    def p2p_merges(self):
+        st = self._state()
+        return int(st.comm_ctx.p2p_merges) if st.comm_ctx is not None else 0
 
     def _make(self, name):
         def call(db):
@@ -492,43 +678,64 @@ class CompiledModule:
             consts.append(d.index(lit) if lit in d else -1)
         a = Args()
         carr = (Col * max(1, len(cols)))()
+        D = dist_config()
+        multi = D is not None and D.world > 1
         for i, c in enumerate(cols):
             mn, mx, flags = c.min, c.max, 0
             arg, cname, rep = q["inputs"][i]
-            if DIST is not None and DIST.world > 1 and arg in DIST.partitioned:
-                if cname in DIST.partkeys:
+            if multi and arg in D.partitioned:
+                if cname in D.partkeys:
                     flags = 1  # tables keyed by the partitioning column stay rank-local: local value range suffices
                 elif rep == "i32":
-                    mn, mx = DIST.global_range((name, i), mn, mx)
+                    mn, mx = D.global_range((name, i), mn, mx)
             carr[i] = Col(c.ptr, c.rows, mn, mx, c.width, KIND_ID[c.kind], flags, 0)
-        if DIST is not None and DIST.world > 1:
-            a.part_mask = sum(1 << i for i, g in enumerate(q["args"]) if g in DIST.partitioned)
         narr = (ctypes.c_int64 * max(1, len(nrows)))(*nrows)
+        garr = None
+        if multi:
+            a.part_mask = sum(1 << i for i, g in enumerate(q["args"]) if g in D.partitioned)
+            # rank-independent row counts: tables merged across ranks are planned from them (all ranks agree)
+            garr = (ctypes.c_int64 * max(1, len(nrows)))(*[
+                D.global_rows((name, g), nrows[i]) if g in D.partitioned else nrows[i] for i, g in enumerate(q["args"])])
+            a.nrows_global = garr
         karr = (ctypes.c_int64 * max(1, len(consts)))(*consts)
         a.cols, a.ncols, a.nargs, a.nrows = carr, len(cols), len(nrows), narr
         a.consts, a.nconsts = karr, len(consts)
-        return a, (cols, carr, narr, karr)
+        return a, (cols, carr, narr, karr, garr)
 
     def execute(self, name, a, fetch=True, kernel_times=False, trace=False):
         be = backend()
+        st = self._state()
         a.flags = (0 if fetch else F_NOFETCH) | (F_KERNEL_TIMES if kernel_times else 0) | (F_TRACE if trace else 0)
         a.stream = be.stream()
-        a.workspace, a.workspace_bytes = (self.ws[0] if self.ws else None), self.ws_bytes
-        if DIST is not None and DIST.world > 1:
-            if self._merge_cb is None:
-                self._merge_cb = MERGE_FN(self._merge)
-            a.merge = ctypes.cast(self._merge_cb, ctypes.c_void_p)
-            a.rank, a.world = DIST.rank, DIST.world
+        a.workspace, a.workspace_bytes = (st.ws[0] if st.ws else None), st.ws_bytes
+        D = dist_config()
+        if D is not None and D.world > 1:
+            a.rank, a.world = D.rank, D.world
+            if D.comm is not None:
+                # the product path: the generated module calls the exchange library directly (plain C, stream ordered)
+                if st.comm_ctx is None:
+                    st.comm_ctx = CommCtx()
+                st.comm_ctx.comm, st.comm_ctx.workspace, st.comm_ctx.stream = D.comm, a.workspace, a.stream
+                a.merge = ctypes.cast(comm_lib().sdqlb200_comm_merge, ctypes.c_void_p)
+                a.merge_ctx = ctypes.cast(ctypes.pointer(st.comm_ctx), ctypes.c_void_p)
+            else:  # no communicator (gloo in the CPU tests): merges through torch.distributed
+                if st.merge_cb is None:
+                    st.merge_cb = MERGE_FN(self._merge)
+                a.merge = ctypes.cast(st.merge_cb, ctypes.c_void_p)
         rc = self.lib.sdqlb200_run(name.encode(), ctypes.byref(a))
         if rc == E_WORKSPACE:
             need = int(a.workspace_needed)
-            self.ws = None
-            self.ws = be.alloc(need + (need >> 3))
-            self.ws_bytes = need + (need >> 3)
-            a.workspace, a.workspace_bytes = self.ws[0], self.ws_bytes
+            st.ws = None
+            st.ws = be.alloc(need + (need >> 3))
+            st.ws_bytes = need + (need >> 3)
+            a.workspace, a.workspace_bytes = st.ws[0], st.ws_bytes
+            if st.comm_ctx is not None:
+                st.comm_ctx.workspace = a.workspace
             rc = self.lib.sdqlb200_run(name.encode(), ctypes.byref(a))
         if rc != 0:
-            extra = " [%r]" % (self.merge_error,) if self.merge_error is not None else ""
+            extra = " [%r]" % (st.merge_error,) if st.merge_error is not None else ""
+            if D is not None and D.comm is not None:
+                extra += " [comm: %s]" % comm_lib().sdqlb200_comm_last_error().decode()
             raise RuntimeError("sdqlb200_run(%s) failed (%d): %s%s" % (name, rc, self.lib.sdqlb200_last_error().decode(), extra))
         return a
 
@@ -546,20 +753,23 @@ class CompiledModule:
         return {n: int(out[i]) for i, n in enumerate(self.STAT_NAMES) if n != "_"}, rc == 1
 
     def _merge(self, ctx, off, count, op):
-        """sdqlb200_merge_fn: all-reduce `count` elements at workspace + off in place (NCCL on GPUs, gloo in tests)."""
+        """sdqlb200_merge_fn for ranks WITHOUT a communicator (gloo, CPU tests of the host logic): all-reduce `count` elements
+        at workspace + off in place through torch.distributed.  With a communicator the generated module calls
+        sdqlb200_comm_merge (csrc/sdqlb200_comm.cu) instead and Python is not involved."""
         try:
             import torch
-            d = DIST.dist
+            D = dist_config()
+            d = D.dist
             ws = self.ws[1]
             t = ws if isinstance(ws, torch.Tensor) else torch.from_numpy(ws)
             if op == 3:
                 self._merge_table(Table.from_address(off))
             elif op == 0:
-                d.all_reduce(t[off:off + 8 * count].view(torch.float64), op=d.ReduceOp.SUM, group=DIST.group)
+                d.all_reduce(t[off:off + 8 * count].view(torch.float64), op=d.ReduceOp.SUM, group=D.group)
             elif op == 1:
-                d.all_reduce(t[off:off + 8 * count].view(torch.int64), op=d.ReduceOp.SUM, group=DIST.group)
+                d.all_reduce(t[off:off + 8 * count].view(torch.int64), op=d.ReduceOp.SUM, group=D.group)
             else:
-                d.all_reduce(t[off:off + 4 * count].view(torch.int32), op=d.ReduceOp.MIN, group=DIST.group)
+                d.all_reduce(t[off:off + 4 * count].view(torch.int32), op=d.ReduceOp.MIN, group=D.group)
             self.merges += 1
             return 0
         except Exception as e:  # never let an exception cross the C boundary
@@ -574,7 +784,8 @@ class CompiledModule:
         4. all-gather of the combined entries; every rank writes them back into its own table (fields := global sums,
            entries owned by another rank get rep = -2: visible to probes, skipped when the table is iterated)"""
         import torch
-        d, world, rank = DIST.dist, DIST.world, DIST.rank
+        D = dist_config()
+        d, world, rank = D.dist, D.world, D.rank
         dev = self.ws[1].device if isinstance(self.ws[1], torch.Tensor) else torch.device("cpu")
         st = backend().stream()
         L, W = self.lib, 2 + int(t.nfields)
@@ -596,11 +807,11 @@ class CompiledModule:
 
         send, cnt = pack(t, world, None)
         rcnt = torch.empty(world, dtype=torch.int64, device=dev)
-        d.all_to_all_single(rcnt, cnt.to(dev), group=DIST.group)
+        d.all_to_all_single(rcnt, cnt.to(dev), group=D.group)
         rcnt = rcnt.cpu()
         nrecv = int(rcnt.sum())
         recv = torch.empty((max(nrecv, 1), W), dtype=torch.int64, device=dev)
-        d.all_to_all_single(recv[:nrecv], send[:int(cnt.sum())], rcnt.tolist(), cnt.tolist(), group=DIST.group)
+        d.all_to_all_single(recv[:nrecv], send[:int(cnt.sum())], rcnt.tolist(), cnt.tolist(), group=D.group)
         # combine at the destination
         cap2 = 1024
         while cap2 < 2 * nrecv:
@@ -617,22 +828,41 @@ class CompiledModule:
         m = int(m[0])
         # all-gather of the combined runs (padded to the longest)
         sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        d.all_gather(sizes, torch.tensor([m], dtype=torch.int64, device=dev), group=DIST.group)
+        d.all_gather(sizes, torch.tensor([m], dtype=torch.int64, device=dev), group=D.group)
         sizes = [int(x) for x in sizes]
-        if 2 * sum(sizes) > int(t.cap):
+        if 2 * sum(sizes) > int(t.cap):  # the sizes are known to every rank alike: all ranks fail together
             raise RuntimeError("merged dictionary has %d entries, the table was sized for %d slots" % (sum(sizes), int(t.cap)))
         mx = max(max(sizes), 1)
         padded = torch.zeros((mx, W), dtype=torch.int64, device=dev)
         padded[:m] = mine[:m]
         parts = [torch.empty((mx, W), dtype=torch.int64, device=dev) for _ in range(world)]
-        d.all_gather(parts, padded, group=DIST.group)
+        d.all_gather(parts, padded, group=D.group)
         for r in range(world):
             ck(L.sdqlb200_table_absorb(ctypes.byref(t), parts[r].data_ptr(), sizes[r], 1, rank, None, st), "table_absorb")
-        self.table_merges = getattr(self, "table_merges", 0) + 1
+        self.table_merges += 1
 
-    def run(self, name, db):
+    def ensure_workspace(self, name, a):
+        """size the workspace with a dry run (no kernel is launched) so that execute() allocates nothing"""
+        st = self._state()
+        a.flags, a.stream, a.workspace, a.workspace_bytes = F_NOFETCH, backend().stream(), None, 0
+        rc = self.lib.sdqlb200_run(name.encode(), ctypes.byref(a))
+        if rc != E_WORKSPACE:
+            raise RuntimeError("sdqlb200_run(%s) dry run failed (%d): %s" % (name, rc, self.lib.sdqlb200_last_error().decode()))
+        need = int(a.workspace_needed)
+        if st.ws is None or st.ws_bytes < need:
+            st.ws = None
+            st.ws = backend().alloc(need + (need >> 3))
+            st.ws_bytes = need + (need >> 3)
+
+    def run(self, name, db, sync=None):
+        """``sync``: called between the preparation (uploads, workspace) and the execution -- the N-GPU engine passes a
+        barrier: no rank allocates device memory while a peer's merge kernel may be waiting for it"""
         h2d0 = STORE.h2d_bytes
         a, keep = self.prepare(name, db)
+        if sync is not None:
+            self.ensure_workspace(name, a)
+            backend().sync()
+            sync()
         self.execute(name, a)
         q = self.queries[name]
         res = a.result
@@ -643,15 +873,14 @@ class CompiledModule:
         info.device_ms, info.launches, info.tier = float(a.device_ms), int(a.launches), int(a.tier)
         info.workspace_bytes, info.h2d_bytes, info.d2h_bytes, info.rows = int(a.workspace_needed), STORE.h2d_bytes - h2d0, 8 + n * nf * 8, n
         self.last = info
-        if int(a.result_partial) and DIST is not None and DIST.world > 1 and q["result_kind"] == "rows":
+        D = dist_config()
+        if int(a.result_partial) and D is not None and D.world > 1 and q["result_kind"] == "rows":
             # every group was emitted by exactly one (owner) rank: concatenate the ranks' columns.  String fields that
             # reference rows of a partitioned relation are decoded before they leave the rank that owns those rows.
             for j, (fname, fk) in enumerate(q["result"]):
-                if fk.startswith("str:ref:") and fk.split(":")[2] in DIST.partitioned:
+                if fk.startswith("str:ref:") and fk.split(":")[2] in D.partitioned:
                     raise NotImplementedError("string result field from a partitioned relation across GPUs")
-            parts = [None] * DIST.world
-            DIST.dist.all_gather_object(parts, cols, group=DIST.group)
-            cols = [np.concatenate([p[j] for p in parts]) for j in range(nf)]
+            cols = D.gather_rows(cols)
             n = len(cols[0]) if cols else 0
             info.rows = n
         return self.box(q, db, cols, n, keep[0])
@@ -715,6 +944,249 @@ def stub_entry(mod, name):
         return res
     call.__name__ = name + "_compiled"
     return call
+
+
+# ---------------------------------------------------------------------------------------------
+# one process, N GPUs: what sdqlpy_init(mode, N) sets up (N = the reference's TBB thread count, sdql_lib.py:372-387)
+# ---------------------------------------------------------------------------------------------
+class _ThreadCollectives:
+    """the three torch.distributed calls CompiledModule._merge / _merge_table make, between the threads of an Engine that
+    has no communicator -- i.e. under the emulation back end in the CPU tests of the host logic; never on a GPU."""
+
+    class ReduceOp:
+        SUM, MIN, MAX = "sum", "min", "max"
+
+    def __init__(self, td):
+        self.td = td
+
+    def _x(self, obj):
+        return self.td.engine.exchange(self.td.rank, obj)
+
+    def all_reduce(self, t, op="sum", group=None):
+        import torch
+        parts = self._x(t.clone())
+        acc = parts[0].clone()
+        for p_ in parts[1:]:
+            acc = acc + p_ if op == "sum" else (torch.minimum(acc, p_) if op == "min" else torch.maximum(acc, p_))
+        t.copy_(acc)
+
+    def all_to_all_single(self, out, inp, out_splits=None, in_splits=None, group=None):
+        import torch
+        W = self.td.world
+        if in_splits is None:
+            in_splits = [inp.shape[0] // W] * W
+        sent = self._x(list(torch.split(inp.clone(), in_splits)))
+        got = torch.cat([sent[s][self.td.rank] for s in range(W)])
+        out.copy_(got.reshape(out.shape))
+
+    def all_gather(self, outs, t, group=None):
+        for o, p_ in zip(outs, self._x(t.clone())):
+            o.copy_(p_)
+
+
+class ThreadDist(DistConfig):
+    """one rank of an Engine: the communicator comes from sdqlb200_comm_create_all, the (rare) host-side exchanges --
+    global column ranges on a query's first call, concatenation of result rows -- go through shared memory."""
+
+    def __init__(self, engine, rank, comm, partitioned, partkeys):
+        self.engine, self.rank, self.world, self.comm = engine, rank, engine.n, comm
+        self.partitioned, self.partkeys = set(partitioned), set(partkeys)
+        self.stats, self.group, self.p2p = {}, None, comm is not None
+        self.dist = _ThreadCollectives(self) if comm is None else None  # only the CPU tests run without a communicator
+
+    def host_max(self, values):
+        allv = self.engine.exchange(self.rank, list(values))
+        return [max(v[i] for v in allv) for i in range(len(values))]
+
+    def gather_rows(self, cols):
+        parts = self.engine.exchange(self.rank, cols)
+        return [np.concatenate([p_[j] for p_ in parts]) for j in range(len(cols))]
+
+
+class Engine:
+    """N GPUs driven by N host threads of this process.  Relations named in ``partitioned`` are range partitioned: the
+    cut points are taken on the column listed in ``partkeys`` (the relation must be sorted by it), so relations that share
+    key values -- lineitem / orders on the order key -- are co-partitioned and their join stays GPU-local; a partitioned
+    relation without such a column is cut into equal row ranges.  ``partitioned=None``: per query, the argument with the
+    most rows.  Everything else is replicated.  Partial dictionaries are merged on the devices (sdqlb200_comm.h)."""
+
+    def __init__(self, ngpus, partitioned=("li", "ord"), partkeys=("l_orderkey", "o_orderkey"), _test_backend=None):
+        import queue
+        self.n, self.partitioned, self.partkeys = ngpus, partitioned, tuple(partkeys)
+        self._test_backend = _test_backend  # tests/ only: emulation back end per thread, merges through Python
+        if _test_backend is None:
+            import torch
+            if not torch.cuda.is_available() or torch.cuda.device_count() < ngpus:
+                raise RuntimeError("sdqlpy_b200: %d GPUs requested, %d visible -- no CPU fallback" %
+                                   (ngpus, torch.cuda.device_count() if torch.cuda.is_available() else 0))
+            L = comm_lib()
+            devs = (ctypes.c_int32 * ngpus)(*range(ngpus))
+            comms = (ctypes.c_void_p * ngpus)()
+            _comm_check(L.sdqlb200_comm_create_all(ngpus, devs, comms), "comm_create_all")
+            self.comms = [ctypes.c_void_p(comms[r]) for r in range(ngpus)]
+        else:
+            self.comms = [None] * ngpus
+        self.barrier = threading.Barrier(ngpus, timeout=600)
+        self.slots = [None] * ngpus
+        self.jobs = [queue.Queue() for _ in range(ngpus)]
+        self.done = queue.Queue()
+        self.cuts, self.slices = {}, {}
+        self.threads = [threading.Thread(target=self._loop, args=(r,), daemon=True) for r in range(ngpus)]
+        for t in self.threads:
+            t.start()
+
+    def exchange(self, rank, obj):
+        """all ranks' objects, in rank order, on every rank"""
+        self.slots[rank] = obj
+        self.barrier.wait()
+        out = list(self.slots)
+        self.barrier.wait()
+        return out
+
+    def _loop(self, r):
+        if self._test_backend is None:
+            import torch
+            torch.cuda.set_device(r)
+            _ctx.backend = CudaBackend()
+        else:
+            _ctx.backend = self._test_backend()
+        _ctx.store = ColumnStore()
+        while True:
+            job = self.jobs[r].get()
+            if job is None:
+                return
+            try:
+                _ctx.dist = job[1]
+                res = job[0]()
+            except BaseException as e:  # noqa: BLE001 -- handed to the caller
+                self.barrier.abort()    # peers waiting in an exchange fail instead of hanging
+                res = e
+            self.done.put((r, res))
+
+    def _key_column(self, q, arg, rel):
+        names = [c for c, _ in q["schemas"][arg]]
+        for k in self.partkeys:
+            if k in names and rel[names.index(k)] is not None:
+                return rel[names.index(k)]
+        return None
+
+    @staticmethod
+    def _values(col):
+        if isinstance(col, DeviceColumn):
+            raise ValueError("Engine partitions HOST columns; device-resident columns belong to one GPU")
+        return col.data if hasattr(col, "kind") else np.asarray(col)
+
+    @staticmethod
+    def _rows(rel):
+        first = [c for c in rel if c is not None][0]
+        return first.data.shape[0] if hasattr(first, "kind") else len(first)
+
+    def partition(self, q, db):
+        """-> (per-rank db, partitioned argument names).  Row ranges and column slices are cached per host column."""
+        args = q["args"]
+        if self.partitioned is None:
+            big = max(range(len(args)), key=lambda i: self._rows(db[i]))
+            parts = {args[big]}
+        else:
+            parts = set(a for a in args if a in self.partitioned)
+        if not parts:
+            return [db] * self.n, parts
+        keycols = {a: self._key_column(q, a, db[args.index(a)]) for a in parts}
+        keyed = [a for a in parts if keycols[a] is not None]
+        bounds = {}
+        cutkeys = None
+        if keyed:
+            drv = min(keyed, key=lambda a: self._rows(db[args.index(a)]))
+            kv = self._values(keycols[drv])
+            ck = (id(keycols[drv]), len(kv), self.n)
+            if ck not in self.cuts:
+                if len(kv) > 1 and not bool(np.all(kv[1:] >= kv[:-1])):
+                    raise ValueError("range partitioning needs relation '%s' sorted by its partitioning column" % drv)
+                self.cuts[ck] = (keycols[drv], [kv[(r * len(kv)) // self.n] for r in range(1, self.n)] if len(kv) else [])
+            cutkeys = self.cuts[ck][1]
+        for a in parts:
+            n = self._rows(db[args.index(a)])
+            if keycols[a] is not None and cutkeys is not None and len(cutkeys) == self.n - 1:
+                kv = self._values(keycols[a])
+                bk = (id(keycols[a]), len(kv), self.n, "b", tuple(int(x) for x in cutkeys))
+                if bk not in self.cuts:
+                    if len(kv) > 1 and not bool(np.all(kv[1:] >= kv[:-1])):
+                        raise ValueError("range partitioning needs relation '%s' sorted by its partitioning column" % a)
+                    self.cuts[bk] = (keycols[a], [0] + [int(np.searchsorted(kv, k, side="left")) for k in cutkeys] + [n])
+                bounds[a] = self.cuts[bk][1]
+            else:
+                bounds[a] = [(r * n) // self.n for r in range(self.n)] + [n]
+        out = []
+        for r in range(self.n):
+            dbr = []
+            for i, a in enumerate(args):
+                if a not in parts:
+                    dbr.append(db[i])
+                    continue
+                lo, hi = bounds[a][r], bounds[a][r + 1]
+                dbr.append([self._slice(c, lo, hi) for c in db[i]])
+            out.append(dbr)
+        return out, parts
+
+    def _slice(self, col, lo, hi):
+        if col is None:
+            return None
+        if isinstance(col, np.ndarray):
+            return col[lo:hi]  # a view: the column store keys it by address, stable across calls
+        k = (id(col), lo, hi)
+        if k not in self.slices:
+            from .tpch.gen import Column
+            self.slices[k] = (col, Column(col.name, col.kind, col.data[lo:hi], col.dictionary, col.width))
+        return self.slices[k][1]
+
+    def run(self, mod, name, db):
+        """``<fn>_compiled(db)`` on all GPUs; -> the merged result (what rank 0 returns)"""
+        q = mod.queries[name]
+        dbs, parts = self.partition(q, db)
+        if self.barrier.broken:
+            self.barrier.reset()
+        for r in range(self.n):
+            D = ThreadDist(self, r, self.comms[r], parts, self.partkeys)
+            D.stats = self.stats_of(r, name, parts)
+            self.jobs[r].put((lambda r=r: mod.run(name, dbs[r], sync=self.barrier.wait), D))
+        res = [None] * self.n
+        for _ in range(self.n):
+            r, v = self.done.get()
+            res[r] = v
+        errs = [v for v in res if isinstance(v, BaseException)]
+        if errs:
+            first = [e for e in errs if not isinstance(e, threading.BrokenBarrierError)] or errs
+            raise first[0]
+        self.last = res
+        return res[0]
+
+    def stats_of(self, r, name, parts):
+        """global column ranges / row counts are properties of (rank, query, partitioning): computed once"""
+        if not hasattr(self, "_stats"):
+            self._stats = {}
+        return self._stats.setdefault((r, name, tuple(sorted(parts))), {})
+
+    def each(self, fn):
+        """run fn(rank) on every GPU thread (warm-up, timing, clearing the column stores); -> results in rank order"""
+        for r in range(self.n):
+            self.jobs[r].put((lambda r=r: fn(r), None))
+        res = [None] * self.n
+        for _ in range(self.n):
+            r, v = self.done.get()
+            res[r] = v
+        for v in res:
+            if isinstance(v, BaseException):
+                raise v
+        return res
+
+    def close(self):
+        for r in range(self.n):
+            self.jobs[r].put(None)
+        for t in self.threads:
+            t.join(timeout=10)
+        for c in self.comms:
+            if c is not None:
+                comm_lib().sdqlb200_comm_destroy(c)
 
 
 _modules = {}

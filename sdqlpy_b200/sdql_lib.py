@@ -259,20 +259,41 @@ def table_from_columns(headers, data):
 # --------------------------------------------------------------------------------------------
 # init / dispatch (lib:372-435)
 # --------------------------------------------------------------------------------------------
-_state = {"mode": 0, "gpus": 1}
+_state = {"mode": 0, "gpus": 1, "engine": None, "partitioned": ("li", "ord"), "partkeys": ("l_orderkey", "o_orderkey")}
 
 
 def sdqlpy_init(execution_mode=0, threads_count=1):
     """0: run in Python | 1: compile (IR -> CUDA -> nvcc) and run on B200 | 2: run the previously compiled module.
-    ``threads_count`` (TBB threads in the reference) is the number of GPUs here."""
+    ``threads_count`` (TBB threads in the reference, fixed for the run, lib:372-387) is the number of GPUs here: with
+    N > 1 the queries run on N GPUs of this process (runtime.Engine: one host thread per GPU, relations range
+    partitioned, partial dictionaries merged over NVLink)."""
     if execution_mode not in (0, 1, 2):
         print("Execution mode is not supported. Failed.")
         return
-    _state["mode"], _state["gpus"] = execution_mode, threads_count
+    if _state["engine"] is not None and _state["engine"].n != threads_count:
+        _state["engine"].close()
+        _state["engine"] = None
+    _state["mode"], _state["gpus"] = execution_mode, int(threads_count)
     if execution_mode == 1:
         caller = inspect.stack()[1][0].f_code.co_filename
         from . import build
         build.compile_file(caller, force=True)
+
+
+def set_partitioning(partitioned=("li", "ord"), partkeys=("l_orderkey", "o_orderkey")):
+    """extension (no reference counterpart): which relation arguments the multi-GPU engine range partitions and on which
+    columns; ``partitioned=None`` = per query the argument with the most rows.  Default: the TPC-H workload's names."""
+    _state["partitioned"], _state["partkeys"] = partitioned, tuple(partkeys)
+    if _state["engine"] is not None:
+        _state["engine"].close()
+        _state["engine"] = None
+
+
+def _engine():
+    if _state["gpus"] > 1 and _state["engine"] is None:
+        from . import runtime
+        _state["engine"] = runtime.Engine(_state["gpus"], _state["partitioned"], _state["partkeys"])
+    return _state["engine"] if _state["gpus"] > 1 else None
 
 
 def sdql_compile(in_type):
@@ -288,6 +309,9 @@ def sdql_compile(in_type):
                 print("Error: the compiled version of " + func.__name__ + " is not found!")
                 return None
             db = [a["data"] for a in args]  # columnar layout (lib:420-424)
+            eng = _engine()
+            if eng is not None:
+                return eng.run(mod, func.__name__, db)
             return getattr(mod, fname)(db)
         wrapper.__sdql_in_type__ = in_type
         wrapper.__sdql_func__ = func

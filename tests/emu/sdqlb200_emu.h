@@ -15,7 +15,7 @@
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __restrict__
-#define __shared__ static
+#define __shared__ static thread_local  // per host thread: the N-rank engine tests run one emulated "GPU" per thread
 
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 static emu_dim3 threadIdx_emu0;
@@ -53,7 +53,7 @@ template <class T> static inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *
 using std::max;
 using std::min;
 
-static unsigned long long emu_dyn_smem[1 << 16];
+static thread_local unsigned long long emu_dyn_smem[1 << 16];
 #define SDQL_EXTERN_SMEM(name) unsigned long long* name = emu_dyn_smem
 #define SDQL_LAUNCH(kernel, grid, block, smem, stream, ...) kernel(__VA_ARGS__)
 #define SDQL_UNUSED(x) (void)(x)

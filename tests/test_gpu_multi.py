@@ -1,0 +1,130 @@
+"""N > 1 on real GPUs (needs >= 2 devices; skipped otherwise): the exchange library (csrc/sdqlb200_comm.cu) under both
+bootstraps -- one process driving N GPUs (runtime.Engine, what sdqlpy_init(mode, N) sets up) and one process per GPU
+(torch.distributed + NCCL id / IPC handles) -- all 22 queries against the reference's golden outputs, and once more with
+every table hashed so that the partial dictionaries go through the hash all-to-all (SDQLB200_MERGE_TABLE) on hardware."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from util import QUERIES, QUERY_SCRIPT, ROOT
+
+pytestmark = pytest.mark.gpu
+
+WORKER = r'''
+import json, os, sys
+root = %(root)r
+for p in (root, root + "/tests", root + "/oracle"):
+    sys.path.insert(0, p)
+import torch
+import ref_runner as rr
+from compare import compare
+from sdqlpy_b200 import runtime
+from util import QUERY_SCRIPT, compact_db, golden
+mode, world, sf, out = sys.argv[1], int(sys.argv[2]), float(sys.argv[3]), sys.argv[4]
+queries = ["q%%d" %% i for i in range(1, 23)]
+gold = golden(sf)
+bad, info = [], {}
+if mode == "engine":
+    mod = runtime.load_compiled(QUERY_SCRIPT)
+    eng = runtime.Engine(world)
+    for q in queries:
+        try:
+            d = compare(eng.run(mod, q, compact_db(sf, rr.QUERY_ARGS[q])), gold[q])
+        except Exception as e:
+            d = "EXC %%r" %% (e,)
+        if d is not None:
+            bad.append((q, d))
+    cnt = eng.each(lambda r: (mod.merges, mod.table_merges, mod.p2p_merges))
+    info = {"merges": [c[0] for c in cnt], "table_merges": [c[1] for c in cnt], "p2p_merges": [c[2] for c in cnt]}
+    eng.close()
+else:
+    import torch.distributed as dist
+    from sdqlpy_b200.tpch.gen import SCHEMAS, TPCH
+    rank = int(os.environ["RANK"])
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    runtime.set_distributed(runtime.DistConfig(partitioned=("li", "ord")))
+    mod = runtime.load_compiled(QUERY_SCRIPT)
+    g = TPCH(sf)
+    per = g.O // world
+    orng = (rank * per, (rank + 1) * per if rank < world - 1 else g.O)
+    tabs = {}
+    for t in SCHEMAS:
+        cols = g.columns(t, None, orng) if t in ("lineitem", "orders") else g.columns(t)
+        tabs[t] = [cols.get(c) for c, _ in SCHEMAS[t]]
+    for q in queries:
+        try:
+            d = compare(mod.run(q, [tabs[t] for t in rr.QUERY_ARGS[q]]), gold[q])
+        except Exception as e:
+            d = "EXC %%r" %% (e,)
+        if d is not None:
+            bad.append((q, d))
+    info = {"merges": mod.merges, "table_merges": mod.table_merges, "p2p_merges": mod.p2p_merges, "p2p": runtime.dist_config().p2p}
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank != 0:
+        sys.exit(0)
+json.dump({"mode": mode, "world": world, "sf": sf, "force_hash": os.environ.get("SDQLB200_FORCE_HASH", "0"), "bad": bad, **info,
+           "gpu": torch.cuda.get_device_name(0)}, open(out, "w"))
+'''
+
+
+def _gpus():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _run(tmp_path, mode, world, sf, env=None, tag=""):
+    if _gpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    out = str(tmp_path / ("res%s.json" % tag))
+    e = dict(os.environ, **(env or {}))
+    if mode == "engine":
+        cmd = [sys.executable, str(script), mode, str(world), str(sf), out]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+               "--master-port", "29741", str(script), mode, str(world), str(sf), out]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=e, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    res = json.load(open(out))
+    keep = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(keep):  # the record of a B200 visit (copied to profiles/ by hand)
+        json.dump(res, open(os.path.join(keep, "r02_multi_%s_w%d%s.json" % (mode, world, tag)), "w"), indent=1)
+    return res
+
+
+def test_engine_two_gpus_all22(tmp_path):
+    """sdqlpy_init(mode, 2)'s engine: one process, two GPUs, peer-memory merges"""
+    res = _run(tmp_path, "engine", 2, 0.05)
+    assert res["bad"] == [], res["bad"]
+    assert min(res["merges"]) > 0 and min(res["p2p_merges"]) > 0 and max(res["table_merges"]) == 0
+
+
+def test_engine_two_gpus_hash_all_to_all(tmp_path):
+    """every table hashed: partial dictionaries are shuffled by key hash, combined at the destination, written back"""
+    res = _run(tmp_path, "engine", 2, 0.05, {"SDQLB200_FORCE_HASH": "1"}, "_hash")
+    assert res["bad"] == [], res["bad"]
+    assert min(res["table_merges"]) > 0
+
+
+def test_process_per_gpu_nccl_all22(tmp_path):
+    """torchrun bootstrap: NCCL id broadcast + IPC-mapped mailboxes"""
+    res = _run(tmp_path, "procs", 2, 0.05)
+    assert res["bad"] == [], res["bad"]
+    assert res["merges"] > 0 and res["p2p"] and res["p2p_merges"] > 0
+
+
+def test_process_per_gpu_hash_all_to_all(tmp_path):
+    res = _run(tmp_path, "procs", 2, 0.05, {"SDQLB200_FORCE_HASH": "1"}, "_hash")
+    assert res["bad"] == [], res["bad"]
+    assert res["table_merges"] > 0
+
+
+def test_engine_four_gpus(tmp_path):
+    res = _run(tmp_path, "engine", 4, 0.05)
+    assert res["bad"] == [], res["bad"]
