@@ -127,6 +127,18 @@ def compile_tbl(force=False):
     return nvcc(src, so)
 
 
+def compile_ingest(force=False):
+    """csrc/sdqlb200_ingest.cu -> sdqlpy_b200/_build/libsdqlb200_ingest.so (reference-layout columns -> resident layout)."""
+    src = os.path.join(CSRC, "sdqlb200_ingest.cu")
+    out_dir = os.path.join(PKG, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libsdqlb200_ingest.so")
+    deps = [src, os.path.join(INC, "sdqlb200_ingest.h"), os.path.join(INC, "sdqlb200.h")]
+    if not force and os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps):
+        return so
+    return nvcc(src, so)
+
+
 def compile_comm(force=False):
     """csrc/sdqlb200_comm.cu -> sdqlpy_b200/_build/libsdqlb200_comm.so (cross-GPU merges: NVLink peer-memory all-reduce,
     NCCL all-reduce, hash all-to-all; NCCL itself is bound at run time with dlopen)."""

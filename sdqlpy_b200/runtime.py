@@ -260,7 +260,10 @@ class ColumnStore:
             return ("np", src.__array_interface__["data"][0], src.nbytes, str(src.dtype))
         return ("obj", id(src))
 
-    def get(self, src, rep, width):
+    def get(self, src, rep, width, shared=None):
+        """``shared``: the rank configuration when the column belongs to a relation that is partitioned across ranks --
+        the dictionary of a dictionary-coded string column is then the union of all ranks' values (merged tables are keyed
+        by the codes, so they must mean the same on every rank)."""
         if isinstance(src, DeviceColumn):
             if src.kind != rep:
                 raise ValueError("device column is '%s', query needs '%s'" % (src.kind, rep))
@@ -268,21 +271,54 @@ class ColumnStore:
         k = (self.key(src), rep, width)
         if self.enabled and k in self.cache:
             return self.cache[k][0]
+        be = backend()
         packed = getattr(src, "wire", None)
         if packed is not None and packed.rep == rep and packed.rows == len(src.data):
             # the column crosses the link in its packed form and is expanded on the device (csrc/sdqlb200_wire.cu)
-            ptr, holder, h2d = backend().upload_packed(packed)
+            ptr, holder, h2d = be.upload_packed(packed)
             self.h2d_bytes += h2d
             w = {"i32": 4, "f64": 8, "code": 1}[rep]
             col = DeviceColumn(rep, ptr, holder, packed.rows, packed.min, packed.max, w, packed.dictionary, packed.rows * w)
         else:
-            img, mn, mx, w, d = _encode(src, rep, width)
-            ptr, holder = backend().upload(img)
-            self.h2d_bytes += img.nbytes
-            col = DeviceColumn(rep, ptr, holder, img.shape[0], mn, mx, w, d, img.nbytes)
+            col = None
+            if isinstance(src, np.ndarray) and be.name == "cuda" and not (rep == "f64" and src.dtype == np.float64):
+                # reference-layout column (int64 / <U n): raw bytes over the link, converted on the device (ingest.py)
+                from . import ingest
+                try:
+                    ptr, holder, mn, mx, w, d, h2d = ingest.upload(src, rep, width, be)
+                    self.h2d_bytes += h2d
+                    col = DeviceColumn(rep, ptr, holder, len(src), mn, mx, w, d, len(src) * (width if rep == "bytes" else w))
+                except ingest.TooManyValues:
+                    col = None  # more distinct strings than the device encoder takes: host dictionary below
+            if col is None:
+                img, mn, mx, w, d = _encode(src, rep, width)
+                ptr, holder = be.upload(img)
+                self.h2d_bytes += img.nbytes
+                col = DeviceColumn(rep, ptr, holder, img.shape[0], mn, mx, w, d, img.nbytes)
+        if shared is not None and rep == "code" and isinstance(src, np.ndarray):
+            self._share_dictionary(col, shared, be)
         if self.enabled:
             self.cache[k] = (col, src)  # keep the host object alive so the identity key stays valid
         return col
+
+    @staticmethod
+    def _share_dictionary(col, D, be):
+        """all ranks' dictionaries -> their sorted union; this rank's codes are rewritten to it"""
+        parts = D.exchange_obj(list(col.dictionary))
+        union = sorted(set().union(*[set(p_) for p_ in parts]))
+        if union == list(col.dictionary):
+            return
+        pos = {v: i for i, v in enumerate(union)}
+        table = np.array([pos[v] for v in col.dictionary] or [0], dtype=np.int32)
+        if be.name == "cuda":
+            from . import ingest
+            col.ptr, col.holder, col.width = ingest.recode(col.holder, col.rows, col.width, table, be)
+        else:
+            codes = table[np.asarray(col.holder).reshape(-1)[:col.rows].astype(np.int64)] if col.rows else np.zeros(0, np.int32)
+            img = codes.astype(np.uint8 if len(union) <= 256 else np.int32)
+            col.ptr, col.holder = be.upload(img)
+            col.width = img.dtype.itemsize
+        col.dictionary, col.min, col.max = union, 0, len(union) - 1
 
     def clear(self):
         self.cache.clear()
@@ -406,6 +442,12 @@ class DistConfig:
         t = torch.tensor(list(values), dtype=torch.int64)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
         return [int(x) for x in t]
+
+    def exchange_obj(self, obj):
+        """all ranks' (small, picklable) objects in rank order, on every rank -- start-up / first call only"""
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, obj, group=self.group)
+        return parts
 
     def global_range(self, key, mn, mx):
         """column statistics must agree on all ranks: merged tables use them as packing radices."""
@@ -661,7 +703,9 @@ class CompiledModule:
             names = [c for c, _ in q["schemas"][arg]]
             kind = dict((c, k) for c, k in q["schemas"][arg])[col]
             width = kind[1] if isinstance(kind, list) else 0
-            cols.append(STORE.get(db[argpos[arg]][names.index(col)], rep, width))
+            Dsh = dist_config()
+            shared = Dsh if (Dsh is not None and Dsh.world > 1 and arg in Dsh.partitioned) else None
+            cols.append(STORE.get(db[argpos[arg]][names.index(col)], rep, width, shared))
         nrows = []
         for a in q["args"]:
             # row count: first available column (the reference reads it from column 0, sdql_compiler.py:644)
@@ -1001,6 +1045,9 @@ class ThreadDist(DistConfig):
     def gather_rows(self, cols):
         parts = self.engine.exchange(self.rank, cols)
         return [np.concatenate([p_[j] for p_ in parts]) for j in range(len(cols))]
+
+    def exchange_obj(self, obj):
+        return self.engine.exchange(self.rank, obj)
 
 
 class Engine:

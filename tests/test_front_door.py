@@ -189,3 +189,21 @@ def test_sdqlpy_init_n_runs_on_n_ranks(user_script, world, monkeypatch):
     finally:
         sdql_lib.sdqlpy_init(0, 1)
         sys.modules.pop("engq%d" % world, None)
+
+
+def test_partitioned_string_dictionaries_agree(user_script):
+    """reference-layout (<U n) string columns of a partitioned relation: every rank dictionary-encodes its own rows, the
+    ranks then agree on the union (codes key the merged tables).  23 lineitems over 3 ranks: no rank sees every flag."""
+    if not rr.available("tpchref_sf1_t1"):
+        pytest.skip("oracle/_ref not built")
+    from util import cut_db
+    mod = runtime.load_compiled(user_script)
+    db = cut_db(ref_db(0.01, ["lineitem"]), ["lineitem"], 23)
+    flags = [set(db[0][8][lo:hi].tolist()) for lo, hi in ((0, 7), (7, 15), (15, 23))]
+    assert len(set(map(frozenset, flags))) > 1  # the ranks' local dictionaries differ
+    want = rr.run(rr.load("tpchref_sf1_t1"), "q1", db)
+    eng = runtime.Engine(3, partitioned=("li",), partkeys=(), _test_backend=emu.EmuBackend)
+    try:
+        assert compare(eng.run(mod, "q1", db), want) is None
+    finally:
+        eng.close()

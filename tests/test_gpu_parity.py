@@ -63,3 +63,56 @@ def test_run_to_run_determinism_of_reductions(mod):
     a = mod.run("q6", db)
     for _ in range(3):
         assert mod.run("q6", db) == a
+
+
+def _needed_ref_db(sf, q, man, cache):
+    """reference-layout db holding only the columns the query touches (TPCH.ref_table puts 1-element placeholders in
+    the other positions: the reference casts every column pointer, sdql_compiler.py:652-668, but never reads those)"""
+    from sdqlpy_b200.tpch.gen import TPCH
+    g = cache.setdefault(("g", sf), TPCH(sf))
+    db = []
+    for arg, t in zip(man["args"], rr.QUERY_ARGS[q]):
+        need = sorted({c for a, c, r in man["inputs"] if a == arg} |
+                      {x.split(":")[3] for _, x in man["result"] if x.startswith("str:") and x.split(":")[2] == arg and len(x.split(":")) > 3})
+        key = (sf, t, tuple(need))
+        if key not in cache:
+            cache[key] = g.ref_table(t, need)
+        db.append(cache[key])
+    return db
+
+
+@pytest.fixture(scope="module")
+def refcache():
+    return {}
+
+
+@pytest.mark.parametrize("q", QUERIES)
+def test_reference_module_sf1(mod, q, refcache):
+    """BASELINE scale SF1 (configs[0] is Q6 at SF1): all 22 queries, the reference's generated C++ (1 thread: its
+    sequential templates, gen:470-517) and the CUDA path on the same reference-layout numpy columns -- which also puts the
+    device-side ingest (int64 / <U n -> resident layout) on the path."""
+    if not rr.available("tpchref_sf1_t1"):
+        pytest.skip("oracle/_ref not built")
+    ref = rr.load("tpchref_sf1_t1")
+    db = _needed_ref_db(1.0, q, mod.queries[q], refcache)
+    want = rr.run(ref, q, db)
+    got = mod.run(q, db)
+    assert compare(got, want) is None
+
+
+@pytest.mark.parametrize("q", ["q1", "q6", "q3", "q5"])
+def test_reference_module_sf10(mod, q):
+    """BASELINE configs[1..2]: Q1, Q3, Q5 (and Q6) at SF10 against the reference module with all host threads (TBB-shim);
+    its multi-threaded dense bool sets race (ref_runner.check), hence the re-tries"""
+    import os
+    if not rr.available("tpchref_sf10_t8"):
+        pytest.skip("oracle/_ref not built")
+    os.environ["SDQL_REF_THREADS"] = str(os.cpu_count() or 8)
+    ref = rr.load("tpchref_sf10_t8")
+    cache = {}
+    db = _needed_ref_db(10.0, q, mod.queries[q], cache)
+    got = mod.run(q, db)
+    d, runs = rr.check(ref, q, db, got, compare)
+    assert d is None, d
+    from sdqlpy_b200 import runtime
+    runtime.STORE.clear()
