@@ -51,7 +51,9 @@ typedef struct {
     int32_t width;    /* element bytes: I32 4, F64 8, CODE 1 or 4, BYTES = fixed string width   */
     int32_t kind;     /* SDQLB200_I32 | F64 | CODE | BYTES                                       */
     int32_t flags;    /* SDQLB200_COL_*                                                          */
-    int32_t reserved;
+    int32_t stride;   /* 0 = no statement.  (log2 B << 16) | K: every value v of this int column satisfies
+                       * (v - min) mod B < K (B a power of two) -- dbgen order keys use 8 of every 32.  Tables keyed by such a
+                       * column pack the holes away: slot (d / B) * K + d mod B, d = v - min (4x fewer slots for order keys) */
 } sdqlb200_col;
 
 /* result rows in SoA form; every field is one 8-byte slot per row (int64 / fp64 bits / string reference) */

@@ -239,7 +239,8 @@ class TableDesc:
         for i in range(self.full_arity):
             if i in self.kept_pos:
                 j = self.kept_pos.index(i)
-                code = "sdqlrt::unpack_part(%s, c.%s_mn[%d], c.%s_rng[%d], c.%s_mul[%d])" % (kk, self.name, j, self.name, j, self.name, j)
+                code = "sdqlrt::unpack_part(%s, c.%s_mn[%d], c.%s_rng[%d], c.%s_mul[%d], c.%s_sb[%d], c.%s_sk[%d])" % (
+                    kk, self.name, j, self.name, j, self.name, j, self.name, j, self.name, j)
                 leaves.append(decode_leaf(self.leaf_kinds[j], code, prov, self.parts[j]))
             else:
                 leaves.append(rep_leaf(i))
@@ -409,7 +410,9 @@ class Kernel:
             # every kernel class.  Group-by kernels keep their tier-0 accumulators in shared memory, so they can afford the
             # register double buffer (q1_k0: 120 registers, 2 CTAs per SM, 6.1-6.7 TB/s against 5.2 TB/s with the L2-prefetch
             # loop); wide scans without a tier use the single buffer + L2 prefetch.  SDQLB200_AUTO_PIPE=l2: the round-1 rule.
-            if AUTO_PIPE == "l2":
+            if AUTO_PIPE == "l2" or self.body2 is not None:
+                # kernels with hit compaction (filter phase + compacted phase) keep the single buffer: Q3 / Q7 / Q9 / Q10 / Q20
+                # are 3-8 % faster with it at SF10 (profiles/r02_visit4/r02_ab_pipes_sf10.json)
                 pipe = "l2" if (self.tiered or len(self.scan_cols) >= 6) else "reg"
             else:
                 pipe = "l2" if (not self.tiered and len(self.scan_cols) >= 6) else "reg"
@@ -638,7 +641,12 @@ class Kernel:
             L.append("    const long long n = c.%s.cap;" % t.name)
             L.append("    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; "
                      "i += (long long)gridDim.x * blockDim.x) {")
-            L.append("        if (c.%s.rep[i] < 0) continue;" % t.name)
+            if iterates_without_rep(self):
+                # entries owned by another rank (rep == -2 after a cross-GPU merge) carry the merged aggregates and a key that
+                # is decoded from the slot alone: every rank can emit them, the result needs no concatenation (c.<t>_all)
+                L.append("        { const int r_ = c.%s.rep[i]; if (r_ == -1 || (r_ < 0 && !c.%s_all)) continue; }" % (t.name, t.name))
+            else:
+                L.append("        if (c.%s.rep[i] < 0) continue;" % t.name)
             L += ["        " + s for s in self.body]
             L.append("    }")
         else:  # single-thread finalisation kernel
@@ -762,6 +770,15 @@ def _render_ring(self):
 
 
 Kernel.render_ring = _render_ring
+
+
+def iterates_without_rep(K):
+    """does kernel K, which iterates a table, get by without the representative source row of the entries it visits (no
+    functionally dependent key part / late-materialised payload re-evaluated there)?  Then any rank can visit any entry."""
+    if K.src[0] != "tbl":
+        return False
+    needle = "rep_of(c.%s, i)" % K.src[1].name
+    return not any(needle in line for line in K.body)
 
 
 # =============================================================================================
@@ -898,8 +915,8 @@ class KeyedSink:
         kk = K.tmp("kk")
         K.emit("unsigned long long %s = 0; bool %s_ok = true;" % (kk, kk))
         for j, code in enumerate(codes):
-            K.emit("%s_ok &= sdqlrt::pack_part(%s, c.%s_mn[%d], c.%s_rng[%d], c.%s_mul[%d], %s);" %
-                   (kk, code, t.name, j, t.name, j, t.name, j, kk))
+            K.emit("%s_ok &= sdqlrt::pack_part(%s, c.%s_mn[%d], c.%s_rng[%d], c.%s_mul[%d], c.%s_sb[%d], c.%s_sk[%d], %s);" %
+                   (kk, code, t.name, j, t.name, j, t.name, j, t.name, j, t.name, j, kk))
         return kk
 
 
@@ -1599,10 +1616,11 @@ class Query:
             kk = K.tmp("lk")
             K.emit("unsigned long long %s = 0; bool %s_ok = true;" % (kk, kk))
             if fast1:
-                K.emit("%s_ok = sdqlrt::pack_key1((int)(%s), c.%s_mn[0], c.%s_rng[0], %s);" % (kk, codes[0], t.name, t.name, kk))
+                K.emit("%s_ok = sdqlrt::pack_key1((int)(%s), c.%s_mn[0], c.%s_rng[0], c.%s_sb[0], c.%s_sk[0], %s);" %
+                       (kk, codes[0], t.name, t.name, t.name, t.name, kk))
             for j, code in enumerate(codes if not fast1 else ()):
-                K.emit("%s_ok &= sdqlrt::pack_part(%s, c.%s_mn[%d], c.%s_rng[%d], c.%s_mul[%d], %s);" %
-                       (kk, code, t.name, j, t.name, j, t.name, j, kk))
+                K.emit("%s_ok &= sdqlrt::pack_part(%s, c.%s_mn[%d], c.%s_rng[%d], c.%s_mul[%d], c.%s_sb[%d], c.%s_sk[%d], %s);" %
+                       (kk, code, t.name, j, t.name, j, t.name, j, t.name, j, t.name, j, kk))
             keyprov = frozenset().union(*[x.prov for x in leaves]) if leaves else E
             tok = self.new_token(t, keyprov if all(x.prov for x in leaves) else None)
             if t.inner is not None:
@@ -1875,7 +1893,7 @@ def mark_iter(q, K, t):
 def _stats_exprs(st):
     """-> (min expr, range expr) in generated host code for a key-part statistics tuple."""
     if st[0] == "col":
-        return "a->cols[%d].min" % st[1], "(a->cols[%d].max - a->cols[%d].min + 1)" % (st[1], st[1])
+        return "a->cols[%d].min" % st[1], "sdqlhost::col_range(a->cols[%d])" % st[1]
     if st[0] == "year":
         return "(a->cols[%d].min / 10000)" % st[1], "(a->cols[%d].max / 10000 - a->cols[%d].min / 10000 + 1)" % (st[1], st[1])
     if st[0] == "range":
@@ -1954,6 +1972,11 @@ def merge_code(q, K):
                      (off % ("c.%s_a%d" % (t.name, j)), cnt, "SDQLB200_SUM_F64" if ct == "f64" else "SDQLB200_SUM_I64"))
             j = k + 1
         L.append("            }")
+        consumers = [K2 for K2 in q.kernels if K2.src == ("tbl", t)]
+        if consumers and all(iterates_without_rep(K2) for K2 in consumers):
+            # the merged table is complete on every rank and its entries are self-contained: every rank iterates all of them,
+            # what is computed from it is not partial any more (no concatenation of result rows, no further merges)
+            L.append("            part_%s = false; c.%s_all = 1;" % (t.name, t.name))
         L.append("        }")
     L.append("    }")
     return L
@@ -1978,9 +2001,11 @@ def render_query(q):
         L.append("    long long k%d;  // %s" % (i, "/".join(str(x) for x in k)))
     for t in q.tables:
         P = max(1, len(t.parts))
-        L.append("    sdqlrt::Tbl %s; long long %s_mn[%d], %s_rng[%d], %s_mul[%d];" % (t.name, t.name, P, t.name, P, t.name, P))
+        L.append("    sdqlrt::Tbl %s; long long %s_mn[%d], %s_rng[%d], %s_mul[%d]; int %s_sb[%d], %s_sk[%d];" %
+                 (t.name, t.name, P, t.name, P, t.name, P, t.name, P, t.name, P))
         for j, (_, ct) in enumerate(t.fields):
             L.append("    %s* %s_a%d;" % (CT[ct], t.name, j))
+        L.append("    int %s_all;  // multi-GPU: the table was merged across ranks and every rank iterates ALL of its entries" % t.name)
     for K in q.kernels:
         if K.body2 is not None:
             L.append("    unsigned %s_qo;  // per-warp queues of surviving row ids: offset in dynamic shared memory" % K.name)
@@ -2048,11 +2073,16 @@ def render_query(q):
         L.append("        void* ag[%d] = {nullptr};" % max(1, nf))
         # presence bits in front of tables that are probed and built selectively (predicates in front of the build)
         t.want_bits = bool(t.probed and t.builder is not None and t.builder.counted and BITS_FILTER)
-        L.append("        if (!sdqlhost::size_table(&c.%s, %d, mn, rng, %s, c.%s_mn, c.%s_rng, c.%s_mul, ar, &tr[%d], %d, ag, %s))" %
-                 (t.name, P, src, t.name, t.name, t.name, ti, nf, "true" if t.want_bits else "false"))
+        L.append("        if (!sdqlhost::size_table(&c.%s, %d, mn, rng, %s, c.%s_mn, c.%s_rng, c.%s_mul, ar, &tr[%d], %d, ag, %s, %s))" %
+                 (t.name, P, src, t.name, t.name, t.name, ti, nf, "true" if t.want_bits else "false",
+                  "true" if t.inner is not None else "false"))
         L.append("            return sdqlhost::fail(SDQLB200_E_ARG, \"%s: key domain of %s does not fit 63 bits\");" % (n, t.name))
         for j, (_, ct) in enumerate(t.fields):
             L.append("        c.%s_a%d = (%s*)ag[%d];" % (t.name, j, CT[ct], j))
+        for j, st_ in enumerate(t.parts):  # strided-dense key columns: the holes of the value range are packed away
+            if st_[0] == "col":
+                L.append("        c.%s_sb[%d] = sdqlhost::col_sb(a->cols[%d]); c.%s_sk[%d] = sdqlhost::col_sk(a->cols[%d]);" %
+                         (t.name, j, st_[1], t.name, j, st_[1]))
         L.append("    }")
     for t in q.tables:
         L.append("    int* own_%s = a->merge ? ar.alloc<int>(c.%s.cap) : nullptr;" % (t.name, t.name))

@@ -64,6 +64,15 @@ static inline unsigned long long bits_min_bytes() {
 
 static inline unsigned long long up256(unsigned long long b) { return (b + 255) & ~255ull; }
 
+// strided-dense key columns (sdqlb200_col.stride): block size 2^sb, residues used sk, and the number of packed values
+static inline int col_sb(const sdqlb200_col& c) { return (c.stride >> 16) & 0xff; }
+static inline int col_sk(const sdqlb200_col& c) { return c.stride & 0xffff; }
+static inline long long col_range(const sdqlb200_col& c) {
+    const int sb = col_sb(c);
+    if (!sb || col_sk(c) < 1) return c.max - c.min + 1;
+    return (((c.max - c.min) >> sb) + 1) * (long long)col_sk(c);
+}
+
 // direct vs hash for `rows` distinct keys at most.  Direct when the dense array is not (much) bigger than what a hash
 // table for `rows` keys would need.  SDQLB200_FORCE_HASH=1 (debug knob): never direct -- exercises the hash build /
 // probe / merge paths at small scale.
@@ -108,7 +117,7 @@ static inline void place_table(sdqlrt::Tbl* t, char* base, TblRegion* r, void** 
 // src_rows bounds the number of distinct keys.  Returns false if the key domain cannot be packed in 63 bits.
 static inline bool size_table(sdqlrt::Tbl* t, int nparts, const long long* mn, const long long* rng,
                               long long src_rows, long long* o_mn, long long* o_rng, long long* o_mul, Arena& ar,
-                              TblRegion* r, int nf, void** aggs, bool want_bits) {
+                              TblRegion* r, int nf, void** aggs, bool want_bits, bool prefix_bits = false) {
     long double dom = 1;
     long long mul = 1;
     for (int j = 0; j < nparts; ++j) {
@@ -136,7 +145,9 @@ static inline bool size_table(sdqlrt::Tbl* t, int nparts, const long long* mn, c
         const long double lim = 2147483648.0L;
         // SDQLB200_BITS_PREFIX=1 (debug knob): composite keys always get the first-part filter (exercised at small scale)
         static const bool force_prefix = getenv("SDQLB200_BITS_PREFIX") && getenv("SDQLB200_BITS_PREFIX")[0] == '1';
-        if (dom <= lim && !(force_prefix && nparts > 1)) r->bdom = (unsigned long long)dom;
+        // prefix_bits: the table is a dictionary of dictionaries probed by its outer key part (one test rejects the whole inner
+        // dictionary, and the per-part bitmap is `inner range` times smaller -- cache resident where the full one is not)
+        if (dom <= lim && !((force_prefix || prefix_bits) && nparts > 1)) r->bdom = (unsigned long long)dom;
         else if (nparts > 1 && o_rng[0] > 0 && (long double)o_rng[0] <= lim) { r->bdom = (unsigned long long)o_rng[0]; r->bmod = r->bdom; }
     }
     r->off = ar.used;

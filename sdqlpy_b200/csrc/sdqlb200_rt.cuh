@@ -249,11 +249,15 @@ SDQL_DEV int tbl_find(const Tbl& t, u64 key, bool ok) {
 // Single-part keys whose part is an int32 column value (the common probe: a foreign key looked up in a table keyed by the
 // primary key): the packed key is the 32-bit offset from the build column's minimum, and the probe needs no 64-bit
 // multiply / modulo.  Same results as pack_part + tbl_find (a single-part table never has a first-part modulus).
-SDQL_DEV bool pack_key1(int x, i64 mn, i64 rng, u64& key) {
+// Strided-dense parts (sdqlb200_col.stride): the column only uses the first `sk` residues of every block of 2^sb values, so
+// the holes are packed away: d -> (d >> sb) * sk + (d & (2^sb - 1)).  sb == 0: plain dense packing.
+SDQL_DEV bool pack_key1(int x, i64 mn, i64 rng, int sb, int sk, u64& key) {
     const int m = (int)mn;  // statistics of an int32 / dictionary-code column
-    const unsigned d = (unsigned)x - (unsigned)m;
+    unsigned d = (unsigned)x - (unsigned)m;
+    bool ok = x >= m;
+    if (sb) { const unsigned lo = d & ((1u << sb) - 1u); ok &= lo < (unsigned)sk; d = (d >> sb) * (unsigned)sk + lo; }
     key = d;
-    return x >= m && (u64)d < (u64)rng;
+    return ok && (u64)d < (u64)rng;
 }
 SDQL_DEV int tbl_find1(const Tbl& t, unsigned d, bool ok) {
     if (!ok) return -1;
@@ -305,15 +309,19 @@ SDQL_DEV int rep_of(const Tbl& t, int slot) {  // safe for slot == -1 (returns a
 }
 
 // mixed-radix key packing: part p in [mn, mn + rng) contributes (p - mn) * mul
-SDQL_DEV bool pack_part(i64 p, i64 mn, i64 rng, i64 mul, u64& key) {
+SDQL_DEV bool pack_part(i64 p, i64 mn, i64 rng, i64 mul, int sb, int sk, u64& key) {
     u64 d = (u64)(p - mn);
+    bool ok = true;
+    if (sb) { const u64 lo = d & ((1ull << sb) - 1ull); ok = lo < (u64)sk; d = (d >> sb) * (u64)sk + lo; }
     key += d * (u64)mul;
-    return d < (u64)rng;
+    return ok && d < (u64)rng;
 }
 
-SDQL_DEV i64 unpack_part(u64 key, i64 mn, i64 rng, i64 mul) {
+SDQL_DEV i64 unpack_part(u64 key, i64 mn, i64 rng, i64 mul, int sb, int sk) {
     if (rng < 0) return (i64)key;  // single unbounded part
-    return (i64)((key / (u64)mul) % (u64)rng) + mn;
+    u64 d = (key / (u64)mul) % (u64)rng;
+    if (sb) d = ((d / (u64)sk) << sb) + d % (u64)sk;
+    return (i64)d + mn;
 }
 SDQL_DEV u64 tbl_key(const Tbl& t, i64 slot) { return t.direct ? (u64)slot : ld1(t.keys + slot); }
 

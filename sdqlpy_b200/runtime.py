@@ -28,7 +28,7 @@ F_TRACE = 4
 
 class Col(ctypes.Structure):
     _fields_ = [("data", ctypes.c_void_p), ("rows", ctypes.c_int64), ("min", ctypes.c_int64), ("max", ctypes.c_int64),
-                ("width", ctypes.c_int32), ("kind", ctypes.c_int32), ("flags", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("width", ctypes.c_int32), ("kind", ctypes.c_int32), ("flags", ctypes.c_int32), ("stride", ctypes.c_int32)]
 
 
 class Result(ctypes.Structure):
@@ -166,11 +166,51 @@ def set_backend(b):
 # columnar store
 # ---------------------------------------------------------------------------------------------
 class DeviceColumn:
-    __slots__ = ("kind", "ptr", "holder", "rows", "min", "max", "width", "dictionary", "nbytes")
+    __slots__ = ("kind", "ptr", "holder", "rows", "min", "max", "width", "dictionary", "nbytes", "stride")
 
-    def __init__(self, kind, ptr, holder, rows, mn, mx, width, dictionary=None, nbytes=0):
+    def __init__(self, kind, ptr, holder, rows, mn, mx, width, dictionary=None, nbytes=0, stride=0):
         self.kind, self.ptr, self.holder, self.rows = kind, ptr, holder, rows
         self.min, self.max, self.width, self.dictionary, self.nbytes = mn, mx, width, dictionary, nbytes
+        self.stride = stride  # sdqlb200_col.stride: (log2 B << 16) | K when (v - min) mod B < K for every value, else 0
+
+
+STRIDE = os.environ.get("SDQLB200_STRIDE", "1") != "0"
+
+
+def stride_stat(values, mn):
+    """sdqlb200_col.stride of an integer column (numpy array or torch tensor): the block size B in {8 .. 128} whose used
+    residues (v - min) mod B fill the smallest prefix [0, K), if that saves at least half of the value range -- dbgen order
+    keys use 8 of every 32.  A strided sample screens the column; a candidate is then verified on EVERY value (a key that
+    broke the rule would be dropped by the packed tables)."""
+    n = len(values)
+    if not STRIDE or n < 1024:
+        return 0
+    is_np = isinstance(values, np.ndarray)
+
+    def residues(v):
+        if is_np:
+            return np.bincount((v.astype(np.int64) - mn) & 127, minlength=128) > 0
+        import torch
+        return (torch.bincount(((v.to(torch.int64) - mn) & 127), minlength=128) > 0).cpu().numpy()
+
+    def best(present):
+        out = (0, 0)
+        for sb in (3, 4, 5, 6, 7):
+            B = 1 << sb
+            K = int(max(r % B for r in np.nonzero(present)[0])) + 1
+            if 2 * K <= B and (out == (0, 0) or K * (1 << out[0]) < out[1] * B):
+                out = (sb, K)
+        return out
+    step = max(1, n // 65536)
+    sb, K = best(residues(values[::step]))
+    if not sb:
+        return 0
+    present = np.zeros(128, dtype=bool)
+    chunk = 1 << 26
+    for lo in range(0, n, chunk):
+        present |= residues(values[lo:lo + chunk])
+    sb, K = best(present)
+    return (sb << 16) | K if sb else 0
 
 
 def _ustr_to_bytes(a, width):
@@ -287,14 +327,16 @@ class ColumnStore:
                 try:
                     ptr, holder, mn, mx, w, d, h2d = ingest.upload(src, rep, width, be)
                     self.h2d_bytes += h2d
-                    col = DeviceColumn(rep, ptr, holder, len(src), mn, mx, w, d, len(src) * (width if rep == "bytes" else w))
+                    col = DeviceColumn(rep, ptr, holder, len(src), mn, mx, w, d, len(src) * (width if rep == "bytes" else w),
+                                       stride_stat(holder[:len(src)], mn) if rep == "i32" else 0)
                 except ingest.TooManyValues:
                     col = None  # more distinct strings than the device encoder takes: host dictionary below
             if col is None:
                 img, mn, mx, w, d = _encode(src, rep, width)
                 ptr, holder = be.upload(img)
                 self.h2d_bytes += img.nbytes
-                col = DeviceColumn(rep, ptr, holder, img.shape[0], mn, mx, w, d, img.nbytes)
+                col = DeviceColumn(rep, ptr, holder, img.shape[0], mn, mx, w, d, img.nbytes,
+                                   stride_stat(img, mn) if rep == "i32" else 0)
         if shared is not None and rep == "code" and isinstance(src, np.ndarray):
             self._share_dictionary(col, shared, be)
         if self.enabled:
@@ -725,14 +767,15 @@ class CompiledModule:
         D = dist_config()
         multi = D is not None and D.world > 1
         for i, c in enumerate(cols):
-            mn, mx, flags = c.min, c.max, 0
             arg, cname, rep = q["inputs"][i]
+            mn, mx, flags, stride = c.min, c.max, 0, (c.stride if rep == "i32" else 0)
             if multi and arg in D.partitioned:
                 if cname in D.partkeys:
                     flags = 1  # tables keyed by the partitioning column stay rank-local: local value range suffices
                 elif rep == "i32":
                     mn, mx = D.global_range((name, i), mn, mx)
-            carr[i] = Col(c.ptr, c.rows, mn, mx, c.width, KIND_ID[c.kind], flags, 0)
+                    stride = 0  # the residue rule is relative to the rank's own minimum: merged tables pack densely
+            carr[i] = Col(c.ptr, c.rows, mn, mx, c.width, KIND_ID[c.kind], flags, stride)
         narr = (ctypes.c_int64 * max(1, len(nrows)))(*nrows)
         garr = None
         if multi:

@@ -96,13 +96,14 @@ class DeviceTPCH:
         return int(off[o1] - off[o0])
 
     def _col(self, kind, tensor, rows, dictionary=None, width=None):
-        mn = mx = 0
+        mn = mx = stride = 0
         if kind == "i32" and rows:
             mn, mx = int(tensor.min()), int(tensor.max())
+            stride = runtime.stride_stat(tensor[:rows], mn)
         elif kind == "code":
             mn, mx = 0, len(dictionary) - 1
         w = {"i32": 4, "f64": 8, "code": 1}.get(kind, width)
-        return runtime.DeviceColumn(kind, tensor.data_ptr(), tensor, rows, mn, mx, w, dictionary, tensor.numel() * tensor.element_size())
+        return runtime.DeviceColumn(kind, tensor.data_ptr(), tensor, rows, mn, mx, w, dictionary, tensor.numel() * tensor.element_size(), stride)
 
     def columns(self, table, cols=None, order_range=None):
         t = self.torch

@@ -207,3 +207,19 @@ def test_partitioned_string_dictionaries_agree(user_script):
         assert compare(eng.run(mod, "q1", db), want) is None
     finally:
         eng.close()
+
+
+def test_stride_statistic_is_verified_on_every_value():
+    """sdqlb200_col.stride: dbgen order keys use 8 of every 32 values -> (log2 32 << 16) | 8; one key that breaks the rule
+    anywhere in the column (missed by the strided sample) must cancel it, or the packed tables would drop that key"""
+    g = TPCH(0.05)
+    ok = g.columns("orders", ["o_orderkey"])["o_orderkey"].data
+    assert runtime.stride_stat(ok, int(ok.min())) == (5 << 16) | 8
+    bad = ok.copy()
+    bad[len(bad) // 2 + 1] += 9            # residue 9..16: outside the first 8 of its block
+    assert runtime.stride_stat(bad, int(bad.min())) in (0, (5 << 16) | 16, (5 << 16) | 15, (5 << 16) | 14, (5 << 16) | 13, (5 << 16) | 12,
+                                                         (5 << 16) | 11, (5 << 16) | 10)
+    assert runtime.stride_stat(bad, int(bad.min())) != (5 << 16) | 8
+    dense = g.columns("customer", ["c_custkey"])["c_custkey"].data
+    assert runtime.stride_stat(dense, int(dense.min())) == 0
+    assert runtime.stride_stat(ok[:100], int(ok.min())) == 0   # too few rows to bother
