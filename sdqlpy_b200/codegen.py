@@ -63,6 +63,9 @@ ROWS_AUTO = os.environ.get("SDQLB200_ROWS_AUTO", "0") == "1"
 # and marks the rows that contain the pattern's first four characters anywhere (sdqlrt::warp_text_scan); the exact
 # per-row search then runs for those candidate rows only
 TEXTSCAN = os.environ.get("SDQLB200_TEXTSCAN", "1") != "0"
+# ... and the exact firstIndex of the candidate rows is computed by the whole warp per (row, pattern)
+# (sdqlrt::warp_text_resolve) instead of by the lane that owns the row; 0 = per-lane str_find on candidate rows
+TEXTRESOLVE = os.environ.get("SDQLB200_TEXTRESOLVE", "1") != "0"
 # Every scan-loop iteration ends with a full-warp sync (all lanes of a warp run the same number of iterations).  Lanes that
 # take a data-dependent slow path (an insertion with its probe loop, a hit behind a probe) otherwise do not rejoin their
 # warp: ncu showed q12_k0's main loop executing with 13 of 32 lanes active and 2.5x the warp-level instructions of the
@@ -555,6 +558,14 @@ class Kernel:
                     toff += 256 * 4 * len(pats)  # (kBlock / kLanes) warps x kTextWords words: at most 256 words per pattern
                     stage.append("        sdqlrt::warp_text_scan<%d>(c.in%d, %s, n, %d, tp%d, tm%d);" %
                                  (len(pats), idx, row0, w, idx, idx))
+                    if TEXTRESOLVE:
+                        # exact positions: kStageRows int16 per warp and pattern behind the masks
+                        L.append("    short* const tx%d = (short*)((unsigned char*)sm + c.%s_to + %du) + (threadIdx.x / sdqlrt::kLanes) * (%d * sdqlrt::kStageRows);" %
+                                 (idx, self.name, toff, len(pats)))
+                        L.append("    const sdqlrt::TextPat tq%d[%d] = {%s};" % (idx, len(pats), ", ".join(text_pat_init(p_) for p_ in pats)))
+                        toff += 8 * 128 * 2 * len(pats)
+                        stage.append("        sdqlrt::warp_text_resolve<%d>(c.in%d, %s, n, %d, tq%d, tm%d, tx%d);" %
+                                     (len(pats), idx, row0, w, idx, idx, idx))
 
             def loop_head(cond):
                 if self.body2 is None:
@@ -770,6 +781,17 @@ def _render_ring(self):
 
 
 Kernel.render_ring = _render_ring
+
+
+def text_pat_init(pat):
+    """C++ initialiser of sdqlrt::TextPat: the pattern as four masked little-endian words + its length"""
+    b = pat.encode("latin1")[:16]
+    ws, ms = [], []
+    for k in range(4):
+        chunk = b[4 * k:4 * k + 4]
+        ws.append(int.from_bytes(chunk, "little"))
+        ms.append(int.from_bytes(b"\xff" * len(chunk), "little"))
+    return "{{%s}, {%s}, %d}" % (", ".join("0x%08xu" % x for x in ws), ", ".join("0x%08xu" % x for x in ms), len(pat))
 
 
 def iterates_without_rep(K):
@@ -1306,6 +1328,17 @@ class Query:
             pats.append(pattern)
         return "sdqlrt::text_cand(tm%d, %d, u & 3)" % (idx, pats.index(pattern))
 
+    def text_position(self, K, s, pattern):
+        """exact firstIndex of ``pattern`` in a string of the scanned row from the warp's cooperative search (None: not
+        available -- no text scan for this string, or the pattern is longer than the 16 characters it handles)"""
+        if not TEXTRESOLVE or len(pattern) > 16:
+            return None
+        cand = self.text_candidate(K, s, pattern)
+        if cand is None:
+            return None
+        idx = self.input(s.arg, s.col, "bytes")
+        return "sdqlrt::text_pos(tx%d, %d, u & 3)" % (idx, K.text_cols[idx][1].index(pattern))
+
     def part_code(self, K, x):
         """by-value key part -> (integer C++ expression, stats)."""
         if isinstance(x, SScalar):
@@ -1818,6 +1851,9 @@ class Query:
             pat, subj = a, self.ev(e.inp3, env, K)
             ptr, w = self.str_ptr(K, subj)
             fn = "str_find" if STRFIND_W else "str_find_bytes"
+            tpos = self.text_position(K, subj, pat.value)
+            if tpos:
+                return SScalar("bool", "(%s >= 0)" % tpos, subj.prov)
             cand = self.text_candidate(K, subj, pat.value)
             if cand and fn == "str_find":
                 fn = "str_find_rare"
@@ -1831,6 +1867,9 @@ class Query:
             if fn == "str_find" and not STRFIND_W:
                 fn = "str_find_bytes"
             code = "sdqlrt::%s(%s, %d, %s, %d)" % (fn, ptr, w, cstr(b.value), len(b.value))
+            tpos = self.text_position(K, a, b.value) if s == XF.FirstIndex else None
+            if tpos:
+                return SScalar("i64", "(long long)" + K.let("int", tpos), a.prov)
             cand = self.text_candidate(K, a, b.value) if s == XF.FirstIndex else None
             if cand:
                 code = "(%s ? %s : -1)" % (cand, code.replace("sdqlrt::str_find(", "sdqlrt::str_find_rare("))
@@ -2129,7 +2168,7 @@ def render_query(q):
                      (K.name, K.name, K.name, K.name, 32 + 1024 * sum(K.byte_cols.values())))
         if K.text_cols:
             L.append("        c.%s_to = (unsigned)((sm_%s + 15) & ~(size_t)15); sm_%s = c.%s_to + %du;" %
-                     (K.name, K.name, K.name, K.name, 1024 * sum(len(pats) for _, pats in K.text_cols.values())))
+                     (K.name, K.name, K.name, K.name, (1024 + (2048 if TEXTRESOLVE else 0)) * sum(len(pats) for _, pats in K.text_cols.values())))
         if ring:
             widths = " + ".join({"i32": "4", "f64": "8", "code": "(size_t)a->cols[%d].width" % idx}[rep]
                                 for (col, rep), (arr, idx) in K.scan_cols.items())

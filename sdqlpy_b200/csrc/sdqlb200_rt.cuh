@@ -169,6 +169,9 @@ SDQL_DEV void stage_rows(unsigned char* dst, const unsigned char* col, i64 row0,
 SDQL_DEV int tx_lane() { return (int)(threadIdx.x & 31u); }
 SDQL_DEV void tx_syncwarp() { __syncwarp(); }
 SDQL_DEV unsigned tx_shfl_down(unsigned v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+SDQL_DEV unsigned tx_shfl(unsigned v, int l) { return __shfl_sync(0xffffffffu, v, l); }
+SDQL_DEV unsigned tx_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+SDQL_DEV int tx_ffs(unsigned v) { return __ffs((int)v); }
 SDQL_DEV void tx_atomic_or(unsigned* p, unsigned v) { atomicOr(p, v); }
 SDQL_DEV void tx_ldnc16(const unsigned char* p, unsigned (&w)[4]) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

@@ -1,8 +1,8 @@
 // sdqlpy-b200 device runtime, part: warp text scan (included by sdqlb200_rt.cuh inside namespace sdqlrt).
 // Kept in a file of its own so that tests/emu/check_textscan.cpp can compile the 32-lane code path on the CPU (one
 // std::thread per lane, barrier-based shuffles) against the scalar definition.  Needs from the includer: SDQL_DEV, i64,
-// kStageRows, ld1<T>(), and -- unless SDQLB200_EMU -- TX_NOINLINE, tx_lane(), tx_syncwarp(), tx_shfl_down(),
-// tx_atomic_or(), tx_ldnc16().
+// kStageRows, ld1<T>(), and -- unless SDQLB200_EMU -- TX_NOINLINE, tx_lane(), tx_syncwarp(), tx_shfl_down(), tx_shfl(),
+// tx_ballot(), tx_ffs(), tx_atomic_or(), tx_ldnc16().
 // ---------------------------------------------------------------------------------------------
 // warp text scan: candidate rows for firstIndex / contains on a scanned string column.
 // The kStageRows rows a warp examines per iteration are one contiguous run of bytes.  All lanes stream the run with
@@ -116,6 +116,108 @@ SDQL_DEV void warp_text_scan(const unsigned char* col, i64 row0, i64 n, int W, c
         for (int p = 0; p < NP; ++p)
             if (win == pat4[p]) { const unsigned r = (unsigned)(q / (size_t)W); mask[p * kTextWords + (r >> 5)] |= 1u << (r & 31u); }
     }
+#endif
+}
+// ---------------------------------------------------------------------------------------------
+// warp text resolve: the exact firstIndex (varchar.h:91-97: wcsstr, the search ends at the row's first NUL) of every
+// pattern in every candidate row of the run, computed by the WHOLE warp per (row, pattern) instead of by the one lane that
+// owns the row.  The per-lane search was 60 % of q13_k0's instructions: ~5 of a warp's 128 rows are candidates, so nearly
+// every iteration sent a few lanes through a ~300-instruction branchy search while the other lanes waited.
+// Lane l examines the start positions 4l .. 4l+3 of the row: its own four characters plus the words of the next lanes
+// (shuffles), compared with the pattern as 1 .. 4 masked words; a ballot picks the first match and the first NUL.  ~50
+// instructions per (row, pattern), no divergence.  Patterns are at most 16 characters (longer ones keep the per-lane search).
+// pos[p * kStageRows + r]: firstIndex of pattern p in row r of the run, -1 = absent.  All lanes must call.
+// ---------------------------------------------------------------------------------------------
+struct TextPat { unsigned w[4], m[4]; int plen; };
+SDQL_DEV unsigned tx_zero_bytes(unsigned x) { return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu); }  // 0x80 per zero byte
+#ifndef SDQLB200_EMU
+template <int NW>
+TX_NOINLINE int warp_str_find(const unsigned char* s, int W, TextPat P) {
+    const int lane = tx_lane();
+    constexpr int kJudge = 32 - NW;  // lanes whose four start positions have all their characters inside this step
+    for (int base = 0; base < W; base += 4 * kJudge) {
+        const int o = base + 4 * lane;
+        unsigned v[NW + 1];
+        v[0] = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (o + j < W) v[0] |= (unsigned)ld1(s + o + j) << (8 * j);  // behind the row's end: NUL
+#pragma unroll
+        for (int k = 1; k <= NW; ++k) v[k] = tx_shfl_down(v[0], k);
+        unsigned hit = 0u;  // bit a: the pattern starts at o + a
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) {
+                const unsigned win = a ? __funnelshift_r(v[k], v[k + 1], 8 * a) : v[k];
+                ok = ok && ((win & P.m[k]) == P.w[k]);
+            }
+            hit |= (ok ? 1u : 0u) << a;
+        }
+        if (lane >= kJudge) hit = 0u;
+        const unsigned z = tx_zero_bytes(v[0]);
+        const unsigned mh = tx_ballot(hit != 0u), mz = tx_ballot(z != 0u);
+        int pos = 0x7fffffff, nul = 0x7fffffff;
+        if (mh) { const int L = tx_ffs(mh) - 1; pos = base + 4 * L + tx_ffs(tx_shfl(hit, L)) - 1; }
+        if (mz) { const int L = tx_ffs(mz) - 1; nul = base + 4 * L + ((tx_ffs(tx_shfl(z, L)) - 1) >> 3); }
+        if (pos < nul) return pos;                      // a match cannot contain a NUL: it lies in front of the first one
+        if (nul < base + 4 * kJudge) return -1;         // the string ends inside the judged positions
+    }
+    return -1;
+}
+#endif
+template <int NP>
+SDQL_DEV void warp_text_resolve(const unsigned char* col, i64 row0, i64 n, int W, const TextPat (&pats)[NP], const unsigned* mask,
+                                short* pos) {
+#ifndef SDQLB200_EMU
+    const int lane = tx_lane();
+#pragma unroll
+    for (int p = 0; p < NP; ++p) reinterpret_cast<unsigned long long*>(pos + p * kStageRows)[lane] = ~0ull;  // this lane's 4 rows: -1
+    tx_syncwarp();
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        if (pats[p].plen > 16) continue;  // not resolved here (the caller keeps the per-lane search for it)
+#pragma unroll 1
+        for (int w = 0; w < kTextWords; ++w) {
+            unsigned m = mask[p * kTextWords + w];  // the same word in every lane
+            while (m) {
+                const int r = w * 32 + tx_ffs(m) - 1;
+                m &= m - 1u;
+                const unsigned char* s = col + (row0 + r) * (i64)W;
+                const int nw = (pats[p].plen + 3) >> 2;
+                const int f = nw == 1 ? warp_str_find<1>(s, W, pats[p]) : nw == 2 ? warp_str_find<2>(s, W, pats[p])
+                            : nw == 3 ? warp_str_find<3>(s, W, pats[p]) : warp_str_find<4>(s, W, pats[p]);
+                if (lane == 0) pos[p * kStageRows + r] = (short)f;
+            }
+        }
+    }
+    tx_syncwarp();
+#else
+    const i64 r1 = row0 + kStageRows < n ? row0 + kStageRows : n;
+    for (int p = 0; p < NP; ++p)
+        for (int r = 0; r < kVec; ++r) {  // the emulated "lane" owns the first kVec rows of its run (text_pos below)
+            pos[p * kStageRows + r] = -1;
+            if (pats[p].plen > 16 || row0 + r >= r1 || !((mask[p * kTextWords + (r >> 5)] >> (r & 31)) & 1u)) continue;
+            const unsigned char* s = col + (row0 + r) * (i64)W;
+            int len = 0;
+            while (len < W && s[len]) ++len;
+            char pat[17];
+            for (int j = 0; j < pats[p].plen; ++j) pat[j] = (char)(pats[p].w[j >> 2] >> (8 * (j & 3)));
+            for (int i = 0; i + pats[p].plen <= len; ++i) {
+                int k = 0;
+                while (k < pats[p].plen && s[i + k] == (unsigned char)pat[k]) ++k;
+                if (k == pats[p].plen) { pos[p * kStageRows + r] = (short)i; break; }
+            }
+        }
+#endif
+}
+// exact firstIndex of pattern p in row u (0 .. kVec-1) of this lane
+SDQL_DEV int text_pos(const short* pos, int p, int u) {
+#ifndef SDQLB200_EMU
+    return pos[p * kStageRows + (tx_lane() << 2) + u];
+#else
+    return pos[p * kStageRows + u];
 #endif
 }
 // candidate bit of row u (0 .. kVec-1) of this lane for pattern p

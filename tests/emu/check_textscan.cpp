@@ -33,6 +33,22 @@ SDQL_DEV unsigned tx_shfl_down(unsigned v, int d) {
     g_bar.arrive_and_wait();
     return r;
 }
+SDQL_DEV unsigned tx_shfl(unsigned v, int l) {
+    g_xchg[t_lane] = v;
+    g_bar.arrive_and_wait();
+    const unsigned r = g_xchg[l & 31];
+    g_bar.arrive_and_wait();
+    return r;
+}
+SDQL_DEV unsigned tx_ballot(bool p) {
+    g_xchg[t_lane] = p ? 1u : 0u;
+    g_bar.arrive_and_wait();
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l) r |= g_xchg[l] << l;
+    g_bar.arrive_and_wait();
+    return r;
+}
+SDQL_DEV int tx_ffs(unsigned v) { return __builtin_ffs((int)v); }
 SDQL_DEV void tx_atomic_or(unsigned* p, unsigned v) { __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 SDQL_DEV void tx_ldnc16(const unsigned char* p, unsigned (&w)[4]) {
     if ((uintptr_t)p & 15) { fprintf(stderr, "unaligned 16-byte load\n"); abort(); }
@@ -74,16 +90,32 @@ static long run_case(int W, long n, const char* const (&pats)[NP], unsigned seed
             if (len >= plen) memcpy(s + rand() % (len - plen + 1), p, plen);
             else if (full_rows == false && rand() % 2) memcpy(s + W - 2 > s ? s + W - 2 : s, p, 2);  // a prefix cut by the row end
         }
+        if (rand() % 8 == 0 && len > 2) s[rand() % len] = 0;  // an embedded NUL: the search ends there (a pattern behind it does not count)
     }
     unsigned pat4[NP];
     for (int p = 0; p < NP; ++p) pat4[p] = pat4_of(pats[p]);
     long bad = 0;
     std::vector<unsigned> mask(NP * kTextWords), want(NP * kTextWords);
+    TextPat tps[NP];
+    for (int p = 0; p < NP; ++p) {
+        const int plen = (int)strlen(pats[p]);
+        tps[p].plen = plen;
+        for (int k = 0; k < 4; ++k) {
+            tps[p].w[k] = tps[p].m[k] = 0;
+            for (int j = 0; j < 4; ++j)
+                if (4 * k + j < plen && 4 * k + j < 16) { tps[p].w[k] |= (unsigned)(unsigned char)pats[p][4 * k + j] << (8 * j); tps[p].m[k] |= 0xffu << (8 * j); }
+        }
+    }
+    alignas(8) short pos[NP * kStageRows];
     for (long row0 = 0; row0 < n + kStageRows; row0 += kStageRows) {  // one extra run behind the end: r1 <= row0
         for (auto& m : mask) m = 0xdeadbeefu;
         std::vector<std::thread> th;
         for (int l = 0; l < 32; ++l)
-            th.emplace_back([&, l] { t_lane = l; warp_text_scan<NP>(col, row0, n, W, pat4, mask.data()); });
+            th.emplace_back([&, l] {
+                t_lane = l;
+                warp_text_scan<NP>(col, row0, n, W, pat4, mask.data());
+                warp_text_resolve<NP>(col, row0, n, W, tps, mask.data(), pos);
+            });
         for (auto& t : th) t.join();
         for (auto& m : want) m = 0;
         const long r1 = row0 + kStageRows < n ? row0 + kStageRows : n;
@@ -103,6 +135,12 @@ static long run_case(int W, long n, const char* const (&pats)[NP], unsigned seed
                 const bool found = naive_find(col + (size_t)r * W, W, pats[p], (int)strlen(pats[p])) >= 0;
                 const bool cand = (mask[p * kTextWords + ((r - row0) >> 5)] >> ((r - row0) & 31)) & 1u;
                 if (found && !cand) { if (bad < 5) printf("MISSED MATCH W=%d row %ld pat %s\n", W, r, pats[p]); ++bad; }
+                // the warp-cooperative exact search: the reference's firstIndex for every row of the run
+                const int wantpos = naive_find(col + (size_t)r * W, W, pats[p], (int)strlen(pats[p]));
+                if (pos[p * kStageRows + (r - row0)] != wantpos) {
+                    if (bad < 5) printf("POSITION MISMATCH W=%d row %ld pat %s: got %d want %d\n", W, r, pats[p], pos[p * kStageRows + (r - row0)], wantpos);
+                    ++bad;
+                }
             }
     }
     munmap(map, span + page);

@@ -24,8 +24,9 @@ import numpy as np  # noqa: E402
 from sdqlpy_b200.tpch.gen import SCHEMAS, TPCH  # noqa: E402
 
 
-def to_reference_layout(dc):
-    """runtime.DeviceColumn -> numpy array as read_csv would have made it"""
+def to_reference_layout(dc, width=None):
+    """runtime.DeviceColumn -> numpy array as read_csv would have made it (strings: <U`width`, the schema's VarChar<N> -- the
+    reference casts the buffer to VarChar<N>*, sdql_compiler.py:652-668, so a narrower numpy dtype would be misread)"""
     import torch
     n = dc.rows
     if dc.kind == "i32":
@@ -33,9 +34,11 @@ def to_reference_layout(dc):
     if dc.kind == "f64":
         return dc.holder[:n].cpu().numpy()
     if dc.kind == "code":
-        w = max(len(s) for s in dc.dictionary)
+        w = width or max(len(s) for s in dc.dictionary)
         return np.array(dc.dictionary, dtype="<U%d" % max(1, w))[dc.holder[:n].cpu().numpy()]
     m = dc.holder[:n].cpu().numpy()  # fixed-width bytes
+    if width and width > m.shape[1]:
+        m = np.pad(m, ((0, 0), (0, width - m.shape[1])))
     return np.ascontiguousarray(m.astype(np.uint32)).view("<U%d" % m.shape[1]).reshape(-1)
 
 
@@ -76,7 +79,7 @@ def main():
                 rel = []
                 for c, k in SCHEMAS[t]:
                     if c in cols and (c in need or c == SCHEMAS[t][0][0]):
-                        rel.append(to_reference_layout(cols[c]))
+                        rel.append(to_reference_layout(cols[c], k[1] if isinstance(k, tuple) else None))
                     elif isinstance(k, tuple):
                         rel.append(np.zeros(1, dtype="<U%d" % k[1]))
                     else:

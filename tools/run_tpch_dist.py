@@ -99,7 +99,8 @@ def main():
         rows = res.tuples() if hasattr(res, "tuples") else res
         row = {"query": q, "sf": a.sf, "n_gpus": world, "latency_ms_wall": float(t[0]), "device_ms": float(t[1]),
                "gen_s": round(gen_s, 1), "result_rows": len(rows) if isinstance(rows, list) else 1,
-               "workspace_MB": round(mod.last.workspace_bytes / 1e6, 1), "merges_total": mod.merges}
+               "workspace_MB": round(mod.last.workspace_bytes / 1e6, 1), "merges_total": mod.merges,
+               "table_merges_total": mod.table_merges, "p2p_merges_total": mod.p2p_merges}
         if rank == 0 and a.check != "none":
             full = TPCH(a.sf)
             t0 = time.time()
