@@ -66,6 +66,9 @@ TEXTSCAN = os.environ.get("SDQLB200_TEXTSCAN", "1") != "0"
 # ... and the exact firstIndex of the candidate rows is computed by the whole warp per (row, pattern)
 # (sdqlrt::warp_text_resolve) instead of by the lane that owns the row; 0 = per-lane str_find on candidate rows
 TEXTRESOLVE = os.environ.get("SDQLB200_TEXTRESOLVE", "1") != "0"
+# patterns of >= 7 characters: the scan compares the run's aligned 32-bit words with the pattern's four 4-character
+# substrings (sdqlrt::warp_text_scan_aligned) instead of every byte window with the first four characters
+TEXTALIGNED = os.environ.get("SDQLB200_TEXTALIGNED", "0") == "1"
 # Every scan-loop iteration ends with a full-warp sync (all lanes of a warp run the same number of iterations).  Lanes that
 # take a data-dependent slow path (an insertion with its probe loop, a hit behind a probe) otherwise do not rejoin their
 # warp: ncu showed q12_k0's main loop executing with 13 of 32 lanes active and 2.5x the warp-level instructions of the
@@ -553,11 +556,18 @@ class Kernel:
                 for idx, (w, pats) in self.text_cols.items():
                     L.append("    unsigned* const tm%d = (unsigned*)((unsigned char*)sm + c.%s_to + %du) + (threadIdx.x / sdqlrt::kLanes) * (%d * sdqlrt::kTextWords);" %
                              (idx, self.name, toff, len(pats)))
-                    L.append("    const unsigned tp%d[%d] = {%s};" % (idx, len(pats), ", ".join(
-                        "0x%08xu /* %s */" % (int.from_bytes(p_[:4].encode("latin1"), "little"), p_[:4].replace("*/", "")) for p_ in pats)))
                     toff += 256 * 4 * len(pats)  # (kBlock / kLanes) warps x kTextWords words: at most 256 words per pattern
-                    stage.append("        sdqlrt::warp_text_scan<%d>(c.in%d, %s, n, %d, tp%d, tm%d);" %
-                                 (len(pats), idx, row0, w, idx, idx))
+                    if TEXTALIGNED and all(len(p_) >= 7 for p_ in pats):
+                        L.append("    const unsigned tp%d[%d][4] = {%s};" % (idx, len(pats), ", ".join(
+                            "{%s}" % ", ".join("0x%08xu" % int.from_bytes(p_[o:o + 4].encode("latin1"), "little") for o in range(4))
+                            for p_ in pats)))
+                        stage.append("        sdqlrt::warp_text_scan_aligned<%d>(c.in%d, %s, n, %d, tp%d, tm%d);" %
+                                     (len(pats), idx, row0, w, idx, idx))
+                    else:
+                        L.append("    const unsigned tp%d[%d] = {%s};" % (idx, len(pats), ", ".join(
+                            "0x%08xu /* %s */" % (int.from_bytes(p_[:4].encode("latin1"), "little"), p_[:4].replace("*/", "")) for p_ in pats)))
+                        stage.append("        sdqlrt::warp_text_scan<%d>(c.in%d, %s, n, %d, tp%d, tm%d);" %
+                                     (len(pats), idx, row0, w, idx, idx))
                     if TEXTRESOLVE:
                         # exact positions: kStageRows int16 per warp and pattern behind the masks
                         L.append("    short* const tx%d = (short*)((unsigned char*)sm + c.%s_to + %du) + (threadIdx.x / sdqlrt::kLanes) * (%d * sdqlrt::kStageRows);" %

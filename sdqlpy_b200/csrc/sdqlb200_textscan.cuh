@@ -119,6 +119,74 @@ SDQL_DEV void warp_text_scan(const unsigned char* col, i64 row0, i64 n, int W, c
 #endif
 }
 // ---------------------------------------------------------------------------------------------
+// aligned-word variant of the scan for patterns of >= 7 characters: an occurrence at byte q covers the 4-byte aligned word
+// at ceil(q / 4) * 4 entirely, and that word then equals the pattern's characters [o, o + 4) for o = 0 .. 3.  So the words of
+// the run are compared as they are loaded (4 constants per pattern, 16 compares per 16 bytes and pattern) -- no byte
+// windows (12 funnel shifts per 16 bytes), no neighbour word, no shuffle.  A word belongs to the row of its first byte; an
+// occurrence inside a row has its aligned word inside that row, so no matching row is missed.  pw[p][o]: characters
+// o .. o+3 of pattern p.  The run starts at a multiple of 4 bytes of the column (row0 is a multiple of kStageRows).
+// ---------------------------------------------------------------------------------------------
+template <int NP>
+SDQL_DEV void warp_text_scan_aligned(const unsigned char* col, i64 row0, i64 n, int W, const unsigned (&pw)[NP][4], unsigned* mask) {
+    static_assert(NP >= 1 && NP * kTextWords <= 32, "at most 8 patterns per column");
+    const i64 r1 = row0 + kStageRows < n ? row0 + kStageRows : n;
+#ifndef SDQLB200_EMU
+    const int lane = tx_lane();
+    tx_syncwarp();
+    if (lane < NP * kTextWords) mask[lane] = 0u;
+    tx_syncwarp();
+    if (r1 <= row0) return;
+    const size_t bytes = (size_t)(r1 - row0) * (size_t)W;
+    const size_t total = (size_t)(n - row0) * (size_t)W;
+    const unsigned char* src = col + row0 * W;
+    const size_t nv = (bytes + 15) >> 4;
+    unsigned nx[4];
+    text_load16(src, (size_t)lane << 4, total, nx);
+    for (size_t kb = 0; kb < nv; kb += 32) {
+        const size_t off = (kb + lane) << 4;
+        const unsigned w[4] = {nx[0], nx[1], nx[2], nx[3]};
+        if (kb + 32 < nv) text_load16(src, off + 512, total, nx);
+        if (off >= bytes) continue;
+        bool hit[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) hit[p] = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int p = 0; p < NP; ++p) hit[p] |= (w[j] == pw[p][o]);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            if (!hit[p]) continue;
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                const unsigned x = j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : w[3];
+                if ((x == pw[p][0] || x == pw[p][1] || x == pw[p][2] || x == pw[p][3]) && off + 4 * j < bytes)
+                    text_mark(mask + p * kTextWords, (off + 4 * j) / (size_t)W);
+            }
+        }
+    }
+    tx_syncwarp();
+#else
+    for (int k = 0; k < NP * kTextWords; ++k) mask[k] = 0u;
+    if (r1 <= row0) return;
+    const size_t bytes = (size_t)(r1 - row0) * (size_t)W, total = (size_t)(n - row0) * (size_t)W;
+    const unsigned char* src = col + row0 * W;
+    const size_t lead = (4 - (size_t)(row0 * W) % 4) % 4;  // the emulated run may start anywhere: words aligned in the COLUMN
+    for (size_t q = lead; q < bytes; q += 4) {
+        unsigned x = 0;
+        for (int j = 0; j < 4; ++j)
+            if (q + j < total) x |= (unsigned)src[q + j] << (8 * j);
+        for (int p = 0; p < NP; ++p)
+            if (x == pw[p][0] || x == pw[p][1] || x == pw[p][2] || x == pw[p][3]) {
+                const unsigned r = (unsigned)(q / (size_t)W);
+                mask[p * kTextWords + (r >> 5)] |= 1u << (r & 31u);
+            }
+    }
+#endif
+}
+// ---------------------------------------------------------------------------------------------
 // warp text resolve: the exact firstIndex (varchar.h:91-97: wcsstr, the search ends at the row's first NUL) of every
 // pattern in every candidate row of the run, computed by the WHOLE warp per (row, pattern) instead of by the one lane that
 // owns the row.  The per-lane search was 60 % of q13_k0's instructions: ~5 of a warp's 128 rows are candidates, so nearly

@@ -130,6 +130,37 @@ static long run_case(int W, long n, const char* const (&pats)[NP], unsigned seed
             }
         for (int k = 0; k < NP * kTextWords; ++k)
             if (mask[k] != want[k]) { if (bad < 5) printf("MASK MISMATCH W=%d n=%ld row0=%ld word %d: got %08x want %08x\n", W, n, row0, k, mask[k], want[k]); ++bad; }
+        // the aligned-word variant (patterns of >= 7 characters): same bits as its scalar definition, no matching row missed
+        bool all7 = true;
+        for (int p = 0; p < NP; ++p) all7 = all7 && strlen(pats[p]) >= 7;
+        if (all7) {
+            unsigned pw[NP][4];
+            for (int p = 0; p < NP; ++p)
+                for (int o = 0; o < 4; ++o) pw[p][o] = pat4_of(pats[p] + o);
+            std::vector<unsigned> am(NP * kTextWords, 0xdeadbeefu), aw(NP * kTextWords, 0u);
+            std::vector<std::thread> th2;
+            for (int l = 0; l < 32; ++l)
+                th2.emplace_back([&, l] { t_lane = l; warp_text_scan_aligned<NP>(col, row0, n, W, pw, am.data()); });
+            for (auto& t : th2) t.join();
+            for (size_t q = (size_t)row0 * W; q < (size_t)r1 * W; q += 4) {  // row0 * W is a multiple of 4
+                unsigned x = 0;
+                for (int j = 0; j < 4; ++j)
+                    if (q + j < bytes) x |= (unsigned)col[q + j] << (8 * j);
+                const long r = (long)(q / W);
+                for (int p = 0; p < NP; ++p)
+                    for (int o = 0; o < 4; ++o)
+                        if (x == pw[p][o]) aw[p * kTextWords + ((r - row0) >> 5)] |= 1u << ((r - row0) & 31);
+            }
+            for (int k = 0; k < NP * kTextWords; ++k)
+                if (am[k] != aw[k]) { if (bad < 5) printf("ALIGNED MASK MISMATCH W=%d n=%ld row0=%ld word %d: got %08x want %08x\n", W, n, row0, k, am[k], aw[k]); ++bad; }
+            for (long r = row0; r < r1; ++r)
+                for (int p = 0; p < NP; ++p)
+                    if (naive_find(col + (size_t)r * W, W, pats[p], (int)strlen(pats[p])) >= 0 &&
+                        !((am[p * kTextWords + ((r - row0) >> 5)] >> ((r - row0) & 31)) & 1u)) {
+                        if (bad < 5) printf("ALIGNED MISSED MATCH W=%d row %ld pat %s\n", W, r, pats[p]);
+                        ++bad;
+                    }
+        }
         for (long r = row0; r < r1; ++r)
             for (int p = 0; p < NP; ++p) {
                 const bool found = naive_find(col + (size_t)r * W, W, pats[p], (int)strlen(pats[p])) >= 0;
