@@ -57,10 +57,10 @@ int sdqlb200_comm_allreduce(sdqlb200_comm* c, void* d_buf, uint64_t count, int32
 /* SDQLB200_MERGE_TABLE: all-reduce of a hashed partial dictionary.  Synchronises the stream twice (run lengths).
  * Fails on EVERY rank alike when the union of the keys does not fit t->cap / 2. */
 int sdqlb200_comm_merge_table(sdqlb200_comm* c, const sdqlb200_table* t, void* stream);
-/* concatenation of the ranks' result rows: every rank contributes `count` rows of `nfields` 8-byte columns (device,
- * column j at d_cols[j]); on return h_total = rows of all ranks and h_out[j] (malloc'ed here, caller frees) holds
+/* concatenation of the ranks' result rows: every rank contributes `count` rows of `nfields` 8-byte columns (column j at
+ * cols[j], in host OR device memory -- the copy direction is inferred from the pointer); on return h_total = rows of all ranks and h_out[j] (malloc'ed here, caller frees) holds
  * column j of all ranks in rank order.  Synchronises the stream. */
-int sdqlb200_comm_gather_rows(sdqlb200_comm* c, const int64_t* const* d_cols, int32_t nfields, int64_t count,
+int sdqlb200_comm_gather_rows(sdqlb200_comm* c, const int64_t* const* cols, int32_t nfields, int64_t count,
                               int64_t** h_out, int64_t* h_total, void* stream);
 /* host-side helpers the bootstrap needs (small; synchronise): max over ranks of n int64 values, in place (HOST buffer) */
 int sdqlb200_comm_host_max(sdqlb200_comm* c, int64_t* h_values, int32_t n, void* stream);

@@ -2128,6 +2128,9 @@ def render_query(q):
         L.append("            return sdqlhost::fail(SDQLB200_E_ARG, \"%s: key domain of %s does not fit 63 bits\");" % (n, t.name))
         for j, (_, ct) in enumerate(t.fields):
             L.append("        c.%s_a%d = (%s*)ag[%d];" % (t.name, j, CT[ct], j))
+        L.append("        if (sdqlhost::debug()) fprintf(stderr, \"[sdqlb200] %s: table %s (%s, %d part(s), %d field(s)): worst case %%s, %%lld slots, domain %%.3Lg, presence bits %%llu%%s\\n\", "
+                 "c.%s.direct ? \"direct\" : \"hash\", (long long)c.%s.cap, tr[%d].dom, tr[%d].bdom, tr[%d].bmod ? \" (first part)\" : \"\");" %
+                 (n, t.name, t.kind, P, nf, t.name, t.name, ti, ti, ti))
         for j, st_ in enumerate(t.parts):  # strided-dense key columns: the holes of the value range are packed away
             if st_[0] == "col":
                 L.append("        c.%s_sb[%d] = sdqlhost::col_sb(a->cols[%d]); c.%s_sk[%d] = sdqlhost::col_sk(a->cols[%d]);" %

@@ -402,7 +402,7 @@ int sdqlb200_comm_merge_table(sdqlb200_comm* c, const sdqlb200_table* t, void* s
     return rc;
 }
 
-int sdqlb200_comm_gather_rows(sdqlb200_comm* c, const int64_t* const* d_cols, int32_t nfields, int64_t count,
+int sdqlb200_comm_gather_rows(sdqlb200_comm* c, const int64_t* const* cols, int32_t nfields, int64_t count,
                               int64_t** h_out, int64_t* h_total, void* stream) {
     if (nfields < 0 || nfields > 32 || count < 0) return COMM_FAIL("comm_gather_rows: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
@@ -422,7 +422,7 @@ int sdqlb200_comm_gather_rows(sdqlb200_comm* c, const int64_t* const* d_cols, in
     i64* d_buf = nullptr;
     SDQL_CUDA(cudaMallocAsync((void**)&d_buf, total * (size_t)nfields * 8, st));
     for (int j = 0; j < nfields; ++j)
-        if (count) SDQL_CUDA(cudaMemcpyAsync(d_buf + (size_t)j * total + off[c->rank], d_cols[j], (size_t)count * 8, cudaMemcpyDeviceToDevice, st));
+        if (count) SDQL_CUDA(cudaMemcpyAsync(d_buf + (size_t)j * total + off[c->rank], cols[j], (size_t)count * 8, cudaMemcpyDefault, st));  // host or device source (UVA)
     SDQL_NCCL(g_nccl.GroupStart());
     for (int j = 0; j < nfields; ++j)
         for (int r = 0; r < W; ++r)

@@ -26,8 +26,10 @@ static inline int fail(int code, const char* fmt, ...) {
 #define SDQL_CUDA(x)                                                                                     \
     do {                                                                                                 \
         cudaError_t e_ = (x);                                                                            \
-        if (e_ != cudaSuccess)                                                                           \
+        if (e_ != cudaSuccess) {                                                                         \
+            cudaGetLastError(); /* reported here: a later cudaGetLastError() must not see it again */    \
             return sdqlhost::fail(SDQLB200_E_CUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+        }                                                                                                \
     } while (0)
 
 // bump allocator over the caller's device workspace; keeps counting past the end so a dry run yields the size
