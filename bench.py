@@ -379,14 +379,13 @@ def main():
 
     def step():
         """one Q1 over the whole database: kernels + merge on every rank, result rows on the host of every rank"""
-        mod.execute(q, a, fetch=True)
-        res = a.result
-        n, nf = int(res.count), int(res.nfields)
-        cols = [np.ctypeslib.as_array(res.cols[j], shape=(max(n, 1),))[:n] for j in range(nf)]
-        if world > 1 and int(a.result_partial):
-            cols = D.gather_rows(cols)
+        mod.execute(q, a, fetch=True)  # returns with the result rows in host memory (a.result.cols, malloc'ed by the module)
+        if world > 1 and int(a.result_partial):  # rows emitted per owner rank: concatenated on every rank (not the case for Q1 / Q6)
+            res = a.result
+            n, nf = int(res.count), int(res.nfields)
+            D.gather_rows([np.ctypeslib.as_array(res.cols[j], shape=(max(n, 1),))[:n] for j in range(nf)])
         mod.lib.sdqlb200_result_free(ct.byref(a.result))
-        return int(a.launches), cols
+        return int(a.launches)
 
     W = max(3, args.warmup)
     for _ in range(W):
@@ -401,7 +400,7 @@ def main():
     launches = 0
     e0.record()
     for _ in range(args.steps):
-        ln, _ = step()
+        ln = step()
         launches += ln + (3 if world > 1 else 0)  # + pack / peer all-reduce / unpack of the 6-slot group table
     e1.record()
     torch.cuda.synchronize()

@@ -2238,11 +2238,17 @@ def render_query(q):
                 scan = "(unsigned long long)c.%s.cap * 12ull" % K.src[1].name
             L.append("    const bool cnt_%s = (%s) >= sdqlhost::count_min_bytes() && (%s) >= sdqlhost::count_min_ratio() * (%s);" %
                      (K.name, tot, tot, scan))
+            # tables merged across ranks are planned for the GLOBAL row count (600 M lineitems -> 2^30 slots, whatever the
+            # predicates let through): they are counted whenever that worst case is big -- a rank-independent rule -- and the
+            # ranks' counts are summed, so every rank re-plans the table alike (Q20 on 2 GPUs: 16.9 ms with the worst-case plan)
+            L.append("    const bool cntm_%s = (%s) >= sdqlhost::count_min_bytes();" % (K.name, tot))
+            L.append("    const bool late_%s = cnt_%s || (a->merge != nullptr && cntm_%s);  // its tables are initialised right before it" %
+                     (K.name, K.name, K.name))
     L.append("    g_trace = (a->flags & SDQLB200_F_TRACE) != 0 || sdqlhost::debug();")
     L.append("    sdqlhost_step(st, nullptr);")
     for t in q.tables:
         K = t.builder
-        guard = "if (!cnt_%s) " % K.name if (K is not None and K.count_ok) else ""
+        guard = "if (!late_%s) " % K.name if (K is not None and K.count_ok) else ""
         L.append("    %sSDQL_CUDA(sdqlhost_init_table(a->workspace, tr[%d], st));" % (guard, t.index))
     L.append("    SDQL_CUDA(cudaMemsetAsync((char*)a->workspace + tail_off, 0, zero_end - tail_off, st));")
     L.append("    sdqlhost_step(st, \"%s:init\");" % n)
@@ -2258,20 +2264,22 @@ def render_query(q):
             cops = []
             for t in owned[K]:
                 cops.append("(" + (" || ".join("((a->cols[%d].flags & SDQLB200_COL_PARTKEY) != 0)" % p_[1] for p_ in t.parts if p_[0] == "col") or "false") + ")")
-            L.append("    // partial tables that are merged across ranks keep the worst-case plan (all ranks must agree on it) and get")
-            L.append("    // no presence filter (the merge adds keys behind its back)")
+            L.append("    // partial tables that are merged across ranks are planned from rank-independent numbers (all ranks must agree on")
+            L.append("    // the plan) and get no presence filter (the merge adds keys behind its back)")
             L.append("    const bool merged_%s = a->merge != nullptr && %s && !(%s);" % (K.name, pe, " && ".join(cops)))
             for t in bits_tabs:
                 L.append("    if (merged_%s) c.%s.bits = nullptr;" % (K.name, t.name))
         if K.count_ok:
-            L.append("    if (cnt_%s) {" % K.name)
+            L.append("    if (late_%s) {" % K.name)
             L.append("        const bool merged_ = merged_%s;" % K.name)
-            L.append("        if (!merged_) {")
+            L.append("        if (merged_ ? cntm_%s : cnt_%s) {" % (K.name, K.name))
             uses_smem = bool(K.byte_cols or K.text_cols or K.body2 is not None)
             if uses_smem:  # same shared-memory layout as the real launch (queues / staging sit behind the tier table)
                 L.append("            sdqlhost_occupancy((const void*)%s<3>, sm_%s);  // raises the dynamic shared memory limit" % (K.name, K.name))
             L.append("            SDQL_LAUNCH(%s<3>, g_%s, sdqlrt::kBlock, %s, st, c);" % (K.name, K.name, "sm_%s" % K.name if uses_smem else "0"))
             L.append("            SDQL_CUDA(cudaGetLastError());")
+            L.append("            if (merged_ && a->merge(a->merge_ctx, (unsigned long long)((char*)(c.tcount + %d) - (char*)a->workspace), 1, SDQLB200_SUM_I64))" % K.count_slot)
+            L.append("                return sdqlhost::fail(SDQLB200_E_ARG, \"merge callback failed\");  // sum over ranks >= keys of the union")
             L.append("            unsigned long long h_cnt = 0;")
             L.append("            SDQL_CUDA(cudaMemcpyAsync(&h_cnt, c.tcount + %d, 8, cudaMemcpyDeviceToHost, st));" % K.count_slot)
             L.append("            SDQL_CUDA(cudaStreamSynchronize(st));")

@@ -88,3 +88,16 @@ def test_world3_hashed_shuffle(emu_so, tmp_path, monkeypatch):
     bad, merges, tmerges = open(out).read().split("\n")
     assert bad == "[]", bad
     assert int(tmerges) > 0
+
+
+def test_world2_merged_tables_are_counted_and_replanned_alike(emu_so, tmp_path, monkeypatch):
+    """cardinality passes forced for every table: tables merged across ranks are counted too, the ranks' counts are summed
+    through the merge callback and every rank re-plans the table from that sum (the same plan everywhere, or the merge
+    collectives would not match) -- results must not change"""
+    monkeypatch.setenv("SDQLB200_COUNT_MIN_BYTES", "0")
+    monkeypatch.setenv("SDQLB200_COUNT_MIN_RATIO", "0")
+    out = str(tmp_path / "res.txt")
+    mp.spawn(_worker, args=(2, emu_so, 29737, SUPPORTED, out), nprocs=2, join=True)
+    bad, merges, tmerges = open(out).read().split("\n")
+    assert bad == "[]", bad
+    assert int(merges) > 0
