@@ -68,7 +68,8 @@ TEXTSCAN = os.environ.get("SDQLB200_TEXTSCAN", "1") != "0"
 TEXTRESOLVE = os.environ.get("SDQLB200_TEXTRESOLVE", "1") != "0"
 # patterns of >= 7 characters: the scan compares the run's aligned 32-bit words with the pattern's four 4-character
 # substrings (sdqlrt::warp_text_scan_aligned) instead of every byte window with the first four characters
-TEXTALIGNED = os.environ.get("SDQLB200_TEXTALIGNED", "0") == "1"
+# (B200, SF100: q13_k0 10.23 ms per-lane search -> 9.58 ms warp resolve -> 7.80 ms + aligned words, profiles/r02_visit7)
+TEXTALIGNED = os.environ.get("SDQLB200_TEXTALIGNED", "1") != "0"
 # Every scan-loop iteration ends with a full-warp sync (all lanes of a warp run the same number of iterations).  Lanes that
 # take a data-dependent slow path (an insertion with its probe loop, a hit behind a probe) otherwise do not rejoin their
 # warp: ncu showed q12_k0's main loop executing with 13 of 32 lanes active and 2.5x the warp-level instructions of the

@@ -96,7 +96,9 @@ __global__ void __launch_bounds__(kBlock) k_ucs4_distinct(const unsigned* __rest
                 k = atomicCAS(keys + s, ~0ull, h);
                 if (k == ~0ull) { atomicAdd(count, 1ull); k = h; }
             }
-            if (k == h) { atomicMin(rep + s, row_base + i); break; }
+            // the representative only ever decreases: a plain read screens the atomic out for all but the first few rows of a
+            // value (600 M rows of a 3-value column otherwise serialise on 3 addresses: 245 ms per 2.4 GB column at SF100)
+            if (k == h) { if (row_base + i < *(volatile i64*)(rep + s)) atomicMin(rep + s, row_base + i); break; }
             s = (s + 1) & m;
         }
     }

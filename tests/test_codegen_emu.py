@@ -121,7 +121,7 @@ def test_ragged_relations_match_reference(emu_module, q):
 
 def test_code_generator_switches_keep_results(tmp_path):
     """the A/B partner builds of the defaults (64-bit row indices, register tier-0 accumulators, L2-prefetch pipeline,
-    PROBE32 / RECONVERGE / TEXTSCAN / TEXTRESOLVE off, TEXTALIGNED on) must reproduce the reference's outputs like the default build.  The code
+    PROBE32 / RECONVERGE / TEXTSCAN / TEXTRESOLVE / TEXTALIGNED off) must reproduce the reference's outputs like the default build.  The code
     generator reads its switches at import, hence the subprocess."""
     import subprocess
     import sys
@@ -144,7 +144,7 @@ for q in qs:
     assert d is None, (q, d)
 print("ok")
 ''' % {"root": os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tmp": str(tmp_path)}
-    for tag, env in (("idx64", {"SDQLB200_IDX32": "0", "SDQLB200_TEXTALIGNED": "1"}),
+    for tag, env in (("idx64", {"SDQLB200_IDX32": "0", "SDQLB200_TEXTALIGNED": "0"}),
                      ("tier0reg", {"SDQLB200_TIER0_SMEM": "0", "SDQLB200_PIPELINE": "l2", "SDQLB200_TEXTRESOLVE": "0"}),
                      ("allreg", {"SDQLB200_PIPELINE": "reg"}),
                      ("plain", {"SDQLB200_PROBE32": "0", "SDQLB200_RECONVERGE": "0", "SDQLB200_TEXTSCAN": "0"})):
