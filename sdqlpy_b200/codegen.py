@@ -265,7 +265,9 @@ class TableDesc:
             vals = []
             for j, (fname, ct) in enumerate(self.fields):
                 ld = "ld1" if slot == "i" else "ldg1"  # sequential when the table itself is being scanned
-                vals.append((fname, SScalar(ct, "sdqlrt::%s(c.%s_a%d + %s)" % (ld, self.name, j, sl), prov=prov)))
+                # an int64 aggregate used as a key part elsewhere: its value range is known once this table is complete
+                vals.append((fname, SScalar(ct, "sdqlrt::%s(c.%s_a%d + %s)" % (ld, self.name, j, sl), prov=prov,
+                                            stats=("agg", self.name, j) if ct == "i64" else None)))
             if self.inner is not None:
                 raise CodegenError("nested dictionary value used as a plain value")
             if self.scalar_value or self.count_only:
@@ -937,7 +939,7 @@ class KeyedSink:
             else:
                 t.key_shape = "scalar"
             t.parts = [p[1] for p in parts]
-            if any(p[0] == "raw" for p in t.parts) and len(t.parts) > 1:
+            if any(p[0] in ("raw", "agg", "union") for p in t.parts) and len(t.parts) > 1:
                 raise CodegenError("%s: key with an unbounded part cannot be packed with other parts" % t.name)
         elif len(t.parts) != len(parts):
             raise CodegenError("%s: inconsistent key shapes" % t.name)
@@ -1773,7 +1775,8 @@ class Query:
         b = b.value() if isinstance(b, SLookup) else b
         if isinstance(a, SScalar) and isinstance(b, SScalar):
             ct = "f64" if "f64" in (a.ctype, b.ctype) else a.ctype
-            return SScalar(ct, "(%s ? %s : %s)" % (as_bool(c), cast_to(a, ct), cast_to(b, ct)), a.prov | b.prov | c.prov)
+            st = ("union", a.stats, b.stats) if (ct == "i64" and a.stats and b.stats) else None
+            return SScalar(ct, "(%s ? %s : %s)" % (as_bool(c), cast_to(a, ct), cast_to(b, ct)), a.prov | b.prov | c.prov, E, st)
         raise CodegenError("conditional expression over non-scalars")
 
     def _arith(self, e, env, K, op):
@@ -1951,6 +1954,28 @@ def _stats_exprs(st):
     return "0ll", "-1ll"
 
 
+def late_domain(t):
+    """single-part key whose value range is only known at run time, from int64 aggregate arrays of other tables (and constant
+    ranges): -> ([(table name, field)], lo, hi of the constant ranges) or None.  The table is laid out as a hash table of raw
+    keys and turned into a direct-indexed one right before its build, when the range turns out small (redomain_table)."""
+    if len(t.parts) != 1 or t.parts[0][0] not in ("agg", "union") or t.inner is not None:
+        return None
+    srcs, lo, hi = [], 0, 0
+
+    def walk(st):
+        nonlocal lo, hi
+        if st[0] == "agg":
+            srcs.append((st[1], st[2]))
+            return True
+        if st[0] == "range":
+            lo, hi = min(lo, st[1]), max(hi, st[2])
+            return True
+        if st[0] == "union":
+            return walk(st[1]) and walk(st[2])
+        return False
+    return (srcs, lo, hi) if walk(t.parts[0]) and srcs else None
+
+
 def part_expr(K):
     if K.src[0] == "rel":
         return "part_%s" % K.name
@@ -2056,6 +2081,8 @@ def render_query(q):
         for j, (_, ct) in enumerate(t.fields):
             L.append("    %s* %s_a%d;" % (CT[ct], t.name, j))
         L.append("    int %s_all;  // multi-GPU: the table was merged across ranks and every rank iterates ALL of its entries" % t.name)
+    if any(late_domain(t) for t in q.tables):
+        L.append("    long long* mm;  // {min, max} of the aggregate values a late key domain comes from")
     for K in q.kernels:
         if K.body2 is not None:
             L.append("    unsigned %s_qo;  // per-warp queues of surviving row ids: offset in dynamic shared memory" % K.name)
@@ -2138,13 +2165,19 @@ def render_query(q):
                          (t.name, j, st_[1], t.name, j, st_[1]))
         L.append("    }")
     for t in q.tables:
-        L.append("    int* own_%s = a->merge ? ar.alloc<int>(c.%s.cap) : nullptr;" % (t.name, t.name))
         nf64 = sum(1 for _, ct in t.fields if ct == "f64")
+        if late_domain(t):  # may become a direct table of up to 65536 slots (redomain_table): merge buffers for that case
+            L.append("    int* own_%s = a->merge ? ar.alloc<int>(c.%s.cap > 65536 ? c.%s.cap : 65536) : nullptr;" % (t.name, t.name, t.name))
+            L.append("    double* mg_%s = a->merge ? ar.alloc<double>(65536ll * %d) : nullptr;" % (t.name, 1 + nf64 + 2 * (len(t.fields) - nf64)))
+            continue
+        L.append("    int* own_%s = a->merge ? ar.alloc<int>(c.%s.cap) : nullptr;" % (t.name, t.name))
         L.append("    double* mg_%s = (a->merge && c.%s.cap <= sdqlrt::kFusedMergeMaxSlots) ? ar.alloc<double>(c.%s.cap * %d) : nullptr;" %
                  (t.name, t.name, t.name, 1 + nf64 + 2 * (len(t.fields) - nf64)))
     L.append("    const unsigned long long tail_off = ar.used;  // scalars, counters, partials: zeroed before every run")
     L.append("    c.sc = ar.alloc<double>(%d); c.cnt = ar.alloc<unsigned>(%d); c.tcount = ar.alloc<unsigned long long>(%d);" %
              (max(1, q.nsc), max(1, q.ncnt), max(1, q.ntcount)))
+    if any(late_domain(t) for t in q.tables):
+        L.append("    c.mm = ar.alloc<long long>(2);")
     # launch plans: aggregation tier, shared memory (tier table + column tile ring), resident CTAs per SM, grid
     for K in q.kernels:
         if K.src[0] == "rel":
@@ -2156,6 +2189,7 @@ def render_query(q):
             L.append("    const long long w_%s = 1;" % K.name)
         ring = K.pipe_mode() == "tma"
         L.append("    int g_%s = 1, tier_%s = 2; size_t sm_%s = 0;" % (K.name, K.name, K.name))
+        plan_start = len(L)
         L.append("    {")
         if K.tiered:
             nf, tn = K.smem_nf, K.smem_tbl
@@ -2199,6 +2233,7 @@ def render_query(q):
         else:
             L.append("        g_%s = sdqlhost::grid_for(w_%s, nb < 8 ? nb : 8, sms);" % (K.name, K.name))
         L.append("    }")
+        K.plan_lines = L[plan_start:]  # emitted again when a table of the kernel gets its key domain at run time
     L.append("    long long npart = 0;")
     pi = 0
     for K in q.kernels:
@@ -2250,6 +2285,8 @@ def render_query(q):
     for t in q.tables:
         K = t.builder
         guard = "if (!late_%s) " % K.name if (K is not None and K.count_ok) else ""
+        if late_domain(t) and K is not None:
+            continue  # laid out and initialised right before its build (key domain known then)
         L.append("    %sSDQL_CUDA(sdqlhost_init_table(a->workspace, tr[%d], st));" % (guard, t.index))
     L.append("    SDQL_CUDA(cudaMemsetAsync((char*)a->workspace + tail_off, 0, zero_end - tail_off, st));")
     L.append("    sdqlhost_step(st, \"%s:init\");" % n)
@@ -2259,6 +2296,46 @@ def render_query(q):
         if K.src[0] == "tbl":  # the source table may have been right-sized since the launch plan was made
             L.append("    { const int g2 = sdqlhost::grid_for(c.%s.cap, 8, sms); if (g2 < g_%s) g_%s = g2; }" %
                      (K.src[1].name, K.name, K.name))
+        for t in owned.get(K, []):
+            ld = late_domain(t)
+            if not ld:
+                continue
+            srcs, lo, hi = ld
+            nf = len(t.fields)
+            L.append("    {   // key domain of %s: value range of %s, known now that %s complete" %
+                     (t.name, ", ".join("%s.a%d" % sj for sj in srcs), "it is" if len(srcs) == 1 else "they are"))
+            for tn_, j in srcs:
+                L.append("        SDQL_LAUNCH(sdqlrt::k_minmax_i64, sdqlhost::grid_for(c.%s.cap, 8, sms), sdqlrt::kBlock, 0, st, (const long long*)c.%s_a%d, c.%s.cap, c.mm);" %
+                         (tn_, tn_, j, tn_))
+            L.append("        SDQL_CUDA(cudaGetLastError());")
+            L.append("        long long h_mm[2] = {0, 0};")
+            L.append("        SDQL_CUDA(cudaMemcpyAsync(h_mm, c.mm, 16, cudaMemcpyDeviceToHost, st));")
+            L.append("        SDQL_CUDA(cudaStreamSynchronize(st));")
+            L.append("        if (h_mm[0] > %dll) h_mm[0] = %dll;" % (lo, lo))
+            L.append("        if (h_mm[1] < %dll) h_mm[1] = %dll;" % (hi, hi))
+            L.append("        if (a->merge) {  // every rank must derive the same plan: min / max over the ranks (int32 pair {min, -max})")
+            L.append("            const bool fits_ = h_mm[0] >= -2000000000ll && h_mm[1] <= 2000000000ll;")
+            L.append("            int h_pr[2] = {fits_ ? (int)h_mm[0] : -2147483647, fits_ ? (int)-h_mm[1] : -2147483647};")
+            L.append("            SDQL_CUDA(cudaMemcpyAsync(c.mm, h_pr, 8, cudaMemcpyHostToDevice, st));")
+            L.append("            if (a->merge(a->merge_ctx, (unsigned long long)((char*)c.mm - (char*)a->workspace), 2, SDQLB200_MIN_I32)) return sdqlhost::fail(SDQLB200_E_ARG, \"merge callback failed\");")
+            L.append("            SDQL_CUDA(cudaMemcpyAsync(h_pr, c.mm, 8, cudaMemcpyDeviceToHost, st));")
+            L.append("            SDQL_CUDA(cudaStreamSynchronize(st));")
+            L.append("            h_mm[0] = h_pr[0]; h_mm[1] = -(long long)h_pr[1];")
+            L.append("        }")
+            L.append("        void* ag[%d] = {%s};" % (max(1, nf), ", ".join("c.%s_a%d" % (t.name, j) for j in range(nf)) or "nullptr"))
+            L.append("        const bool rd_ = sdqlhost::redomain_table(&c.%s, (char*)a->workspace, &tr[%d], h_mm[0], h_mm[1] - h_mm[0] + 1, c.%s_mn, c.%s_rng, c.%s_mul, ag);" %
+                     (t.name, t.index, t.name, t.name, t.name))
+            L.append("        if (sdqlhost::debug()) fprintf(stderr, \"[sdqlb200] %s: key domain of %s [%%lld, %%lld] -> %%s, %%lld slots\\n\", h_mm[0], h_mm[1], c.%s.direct ? \"direct\" : \"hash\", (long long)c.%s.cap);" %
+                     (K.name, t.name, t.name, t.name))
+            for j, (_, ct) in enumerate(t.fields):
+                L.append("        c.%s_a%d = (%s*)ag[%d];" % (t.name, j, CT[ct], j))
+            L.append("        if (rd_) {  // the launch plan of %s again: aggregation tier, shared memory, grid" % K.name)
+            L.append("            tier_%s = 2; sm_%s = 0;" % (K.name, K.name))
+            L += ["        " + x for x in K.plan_lines]
+            L.append("        }")
+            L.append("        SDQL_CUDA(sdqlhost_init_table(a->workspace, tr[%d], st));" % t.index)
+            L.append("        sdqlhost_step(st, \"%s:key-domain\");" % K.name)
+            L.append("    }")
         bits_tabs = [t for t in owned.get(K, []) if getattr(t, "want_bits", False)]
         if K.count_ok or bits_tabs:
             pe = part_expr(K)

@@ -175,6 +175,22 @@ static inline bool replan_table(sdqlrt::Tbl* t, char* base, TblRegion* r, long l
     return true;
 }
 
+// A single-part table whose key is a value read out of another dictionary has no statistics when the workspace is laid out
+// (planned as a hash table of raw 64-bit keys).  Once that dictionary is complete its value range [lo, lo + rng) is known:
+// a small range turns the table into a direct-indexed one in the same region (and lets a group-by take the register /
+// shared-memory tiers).  Keeps the hash plan when the range is large or the dense layout would not fit the reservation.
+static inline bool redomain_table(sdqlrt::Tbl* t, char* base, TblRegion* r, long long lo, long long rng, long long* o_mn,
+                                  long long* o_rng, long long* o_mul, void** aggs) {
+    if (rng < 1 || rng > 65536 || table_bytes(1, rng, r->nf) > r->len) return false;
+    o_mn[0] = lo; o_rng[0] = rng; o_mul[0] = 1;
+    r->dom = (long double)rng;
+    r->bdom = r->bmod = 0;
+    t->direct = 1;
+    t->cap = rng;
+    place_table(t, base, r, aggs);
+    return true;
+}
+
 // tables whose reservation is at least this big get a cardinality pass before they are built
 static inline unsigned long long count_min_bytes() {
     static long long v = -1;

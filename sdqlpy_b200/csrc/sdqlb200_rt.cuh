@@ -328,6 +328,34 @@ SDQL_DEV i64 unpack_part(u64 key, i64 mn, i64 rng, i64 mul, int sb, int sk) {
 }
 SDQL_DEV u64 tbl_key(const Tbl& t, i64 slot) { return t.direct ? (u64)slot : ld1(t.keys + slot); }
 
+// value range of an int64 aggregate array over ALL of its slots (free slots hold 0: whatever slot a lookup reads, its value is
+// inside the range) joined with 0: mm[0] = min(0, values), mm[1] = max(0, values); mm is zeroed by the caller.  Group-bys keyed
+// by a value read out of another dictionary (Q13: customers per order count) get their key domain from it at run time.
+__global__ void k_minmax_i64(const i64* a, i64 n, i64* mm) {
+    i64 lo = 0, hi = 0;
+#ifndef SDQLB200_EMU
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const i64 v = ld1(a + i);
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const i64 l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (lo < 0) atomicMin((long long*)mm, (long long)lo);
+        if (hi > 0) atomicMax((long long*)mm + 1, (long long)hi);
+    }
+#else
+    for (i64 i = 0; i < n; ++i) { lo = a[i] < lo ? a[i] : lo; hi = a[i] > hi ? a[i] : hi; }
+    mm[0] = lo < mm[0] ? lo : mm[0];
+    mm[1] = hi > mm[1] ? hi : mm[1];
+#endif
+}
+
 // presence filter of a finished table: one pass over its slots right after the build kernel (no per-insert atomics in
 // the build).  A warp examines 32 consecutive slots; when their bits fall into one word (direct tables: always, unless
 // the first-part modulus wraps inside the group) the warp issues a single atomicOr.
