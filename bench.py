@@ -313,6 +313,7 @@ def main():
             print(json.dumps(reference_arm(args, nproc, workload)))
         return
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's own lines (version banner, INFO) stay off stdout: ONE JSON line
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
