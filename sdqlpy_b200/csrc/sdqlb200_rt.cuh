@@ -234,12 +234,31 @@ SDQL_DEV u64 hash64(u64 x) {  // splitmix64 finaliser
     return x;
 }
 
-// -> slot or -1.  `ok` = every key part was inside the table's packing range.
-SDQL_DEV int tbl_find(const Tbl& t, u64 key, bool ok) {
-    if (!ok || !tbl_maybe(t, key)) return -1;
-    stat(kStFinds);
-    if (t.direct) { stat(kStFindSlots); return ld1(t.rep + key) != -1 ? (int)key : -1; }  // -2 = present, owned by another rank
-    u64 m = (u64)t.cap - 1, h = hash64(key) & m;
+// Probe of a hashed table (open addressing, linear probing).  SDQLB200_PROBE_SECTOR: the probe examines the whole 32-byte
+// sector the home slot lies in -- four 8-byte keys, two 128-bit loads -- per memory round trip: the sector is what a random
+// 8-byte read moves anyway, and a probe chain of up to four slots inside it resolves without a second dependent load (what
+// a 4-lane cooperative group per key would achieve, without giving up 3 of 4 lanes to it).  Tables have >= 1024 slots
+// (power of two), so a group of four never wraps.
+SDQL_DEV int tbl_probe(const Tbl& t, u64 key) {
+    const u64 m = (u64)t.cap - 1;
+    u64 h = hash64(key) & m;
+#if defined(SDQLB200_PROBE_SECTOR) && !defined(SDQLB200_EMU)
+    for (;;) {
+        stat(kStFindSlots);
+        const u64 base = h & ~3ull;
+        const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(t.keys + base));
+        const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2*>(t.keys + base + 2));
+        const u64 k4[4] = {a.x, a.y, b.x, b.y};
+        const int j0 = (int)(h - base);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < j0) continue;
+            if (k4[j] == key) return (int)(base + j);
+            if (k4[j] == kEmpty) return -1;
+        }
+        h = (base + 4) & m;
+    }
+#else
     for (;;) {
         stat(kStFindSlots);
         u64 k = ld1(t.keys + h);
@@ -247,6 +266,15 @@ SDQL_DEV int tbl_find(const Tbl& t, u64 key, bool ok) {
         if (k == kEmpty) return -1;
         h = (h + 1) & m;
     }
+#endif
+}
+
+// -> slot or -1.  `ok` = every key part was inside the table's packing range.
+SDQL_DEV int tbl_find(const Tbl& t, u64 key, bool ok) {
+    if (!ok || !tbl_maybe(t, key)) return -1;
+    stat(kStFinds);
+    if (t.direct) { stat(kStFindSlots); return ld1(t.rep + key) != -1 ? (int)key : -1; }  // -2 = present, owned by another rank
+    return tbl_probe(t, key);
 }
 
 // Single-part keys whose part is an int32 column value (the common probe: a foreign key looked up in a table keyed by the
@@ -270,15 +298,7 @@ SDQL_DEV int tbl_find1(const Tbl& t, unsigned d, bool ok) {
     }
     stat(kStFinds);
     if (t.direct) { stat(kStFindSlots); return ld1(t.rep + d) != -1 ? (int)d : -1; }
-    const u64 key = d, m = (u64)t.cap - 1;
-    u64 h = hash64(key) & m;
-    for (;;) {
-        stat(kStFindSlots);
-        u64 k = ld1(t.keys + h);
-        if (k == key) return (int)h;
-        if (k == kEmpty) return -1;
-        h = (h + 1) & m;
-    }
+    return tbl_probe(t, (u64)d);
 }
 
 // insert-or-find; `src` becomes the slot's representative if the slot is new.  -> slot
