@@ -42,7 +42,13 @@ SDQL_DEV unsigned text_load4(const unsigned char* src, size_t off, size_t total)
 }
 #endif
 #ifndef SDQLB200_EMU
-TX_NOINLINE void text_mark(unsigned* mask, size_t row) { tx_atomic_or(mask + (row >> 5), 1u << (unsigned)(row & 31u)); }
+// marks the rows of the run that the 16-byte chunk at byte `off` overlaps (two at most when W >= 16)
+SDQL_DEV void text_mark_chunk(unsigned* mask, size_t off, size_t bytes, int W) {
+    const unsigned r0 = (unsigned)(off / (size_t)W);
+    const size_t last = off + 15 < bytes ? off + 15 : bytes - 1;
+    const unsigned r1 = (unsigned)(last / (size_t)W);
+    for (unsigned r = r0; r <= r1; ++r) tx_atomic_or(mask + (r >> 5), 1u << (r & 31u));
+}
 #endif
 template <int NP>
 SDQL_DEV void warp_text_scan(const unsigned char* col, i64 row0, i64 n, int W, const unsigned (&pat4)[NP], unsigned* mask) {
@@ -89,18 +95,10 @@ SDQL_DEV void warp_text_scan(const unsigned char* col, i64 row0, i64 n, int W, c
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             if (!hit[p]) continue;
-            // rare (a few percent of the chunks): find the positions again, one word at a time in a rolled loop -- the
-            // code stays small (the fully unrolled form made the kernel miss the instruction cache)
-#pragma unroll 1
-            for (int j = 0; j < 4; ++j) {
-                const unsigned lo = j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : w[3];
-                const unsigned hi = j == 0 ? w[1] : j == 1 ? w[2] : j == 2 ? w[3] : w[4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const unsigned win = a ? __funnelshift_r(lo, hi, 8 * a) : lo;
-                    if (win == pat4[p] && off + 4 * j + a < bytes) text_mark(mask + p * kTextWords, (off + 4 * j + a) / (size_t)W);
-                }
-            }
+            // a hit (a few percent of the chunks; ~a quarter of the warp steps in Q13): mark the rows this 16-byte chunk overlaps
+            // -- a superset of the rows hit, the resolve behind the scan is exact.  (Finding the hit position again, word by
+            // word, was a third of q13_k0's instructions: one lane in a rolled loop, 31 waiting.)
+            text_mark_chunk(mask + p * kTextWords, off, bytes, W);
         }
     }
     tx_syncwarp();
@@ -158,13 +156,7 @@ SDQL_DEV void warp_text_scan_aligned(const unsigned char* col, i64 row0, i64 n, 
                 for (int p = 0; p < NP; ++p) hit[p] |= (w[j] == pw[p][o]);
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
-            if (!hit[p]) continue;
-#pragma unroll 1
-            for (int j = 0; j < 4; ++j) {
-                const unsigned x = j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : w[3];
-                if ((x == pw[p][0] || x == pw[p][1] || x == pw[p][2] || x == pw[p][3]) && off + 4 * j < bytes)
-                    text_mark(mask + p * kTextWords, (off + 4 * j) / (size_t)W);
-            }
+            if (hit[p]) text_mark_chunk(mask + p * kTextWords, off, bytes, W);
         }
     }
     tx_syncwarp();
@@ -188,51 +180,72 @@ SDQL_DEV void warp_text_scan_aligned(const unsigned char* col, i64 row0, i64 n, 
 }
 // ---------------------------------------------------------------------------------------------
 // warp text resolve: the exact firstIndex (varchar.h:91-97: wcsstr, the search ends at the row's first NUL) of every
-// pattern in every candidate row of the run, computed by the WHOLE warp per (row, pattern) instead of by the one lane that
-// owns the row.  The per-lane search was 60 % of q13_k0's instructions: ~5 of a warp's 128 rows are candidates, so nearly
-// every iteration sent a few lanes through a ~300-instruction branchy search while the other lanes waited.
-// Lane l examines the start positions 4l .. 4l+3 of the row: its own four characters plus the words of the next lanes
-// (shuffles), compared with the pattern as 1 .. 4 masked words; a ballot picks the first match and the first NUL.  ~50
-// instructions per (row, pattern), no divergence.  Patterns are at most 16 characters (longer ones keep the per-lane search).
+// pattern in every candidate row of the run, computed by the WHOLE warp, one candidate row at a time, instead of by the one
+// lane that owns the row.  The per-lane search was 60 % of q13_k0's instructions: ~5 of a warp's 128 rows are candidates,
+// so nearly every iteration sent a few lanes through a ~300-instruction branchy search while the other lanes waited.
+// Lane l examines the start positions 4l .. 4l+3 of the row: its own four characters (one aligned 32-bit load + the next
+// lane's word, shifted into place; zero behind the row's end) plus the following words of the next lanes (shuffles),
+// compared with each pattern that marked the row as 1 .. 4 masked words; ballots pick the first match per pattern and the
+// first NUL (a match counts only in front of it).  No divergence; rows longer than 4 * (32 - 4) characters take several
+// steps.  Patterns are at most 16 characters (longer ones keep the per-lane search).
 // pos[p * kStageRows + r]: firstIndex of pattern p in row r of the run, -1 = absent.  All lanes must call.
 // ---------------------------------------------------------------------------------------------
 struct TextPat { unsigned w[4], m[4]; int plen; };
 SDQL_DEV unsigned tx_zero_bytes(unsigned x) { return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu); }  // 0x80 per zero byte
 #ifndef SDQLB200_EMU
-template <int NW>
-TX_NOINLINE int warp_str_find(const unsigned char* s, int W, TextPat P) {
+// pm: bit p set = pattern p marked this row.  Writes out[p * kStageRows] for those patterns (lane 0).
+template <int NP>
+SDQL_DEV void warp_row_find(const unsigned char* s, int W, const TextPat (&pats)[NP], unsigned pm, short* out) {
     const int lane = tx_lane();
-    constexpr int kJudge = 32 - NW;  // lanes whose four start positions have all their characters inside this step
-    for (int base = 0; base < W; base += 4 * kJudge) {
-        const int o = base + 4 * lane;
-        unsigned v[NW + 1];
-        v[0] = 0u;
+    constexpr int kJudge = 32 - 4;  // lanes whose four start positions have all their (<= 16 + 3) characters inside a step
+    const unsigned a = (unsigned)(size_t)s & 3u;
+    const unsigned* wp = reinterpret_cast<const unsigned*>(s - a);
+    int res[NP];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (o + j < W) v[0] |= (unsigned)ld1(s + o + j) << (8 * j);  // behind the row's end: NUL
+    for (int p = 0; p < NP; ++p) res[p] = -1;
+    for (int base = 0; base < W && pm; base += 4 * kJudge) {
+        // characters o .. o+3 of the row: aligned word wi covers characters 4 wi - a .. 4 wi - a + 3
+        const int wi = (base >> 2) + lane, o = base + 4 * lane;
+        unsigned x = (4 * wi - (int)a < W) ? ld1(wp + wi) : 0u;
+        unsigned xn = tx_shfl_down(x, 1);
+        if (lane == 31) xn = (a && 4 * (wi + 1) - (int)a < W) ? ld1(wp + wi + 1) : 0u;
+        unsigned v[5];
+        v[0] = a ? __funnelshift_r(x, xn, 8u * a) : x;
+        if (o + 4 > W) v[0] = o < W ? (v[0] & ((1u << (8 * (W - o))) - 1u)) : 0u;  // behind the row's end: NUL
 #pragma unroll
-        for (int k = 1; k <= NW; ++k) v[k] = tx_shfl_down(v[0], k);
-        unsigned hit = 0u;  // bit a: the pattern starts at o + a
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            bool ok = true;
-#pragma unroll
-            for (int k = 0; k < NW; ++k) {
-                const unsigned win = a ? __funnelshift_r(v[k], v[k + 1], 8 * a) : v[k];
-                ok = ok && ((win & P.m[k]) == P.w[k]);
-            }
-            hit |= (ok ? 1u : 0u) << a;
-        }
-        if (lane >= kJudge) hit = 0u;
+        for (int k = 1; k <= 4; ++k) v[k] = tx_shfl_down(v[0], k);
         const unsigned z = tx_zero_bytes(v[0]);
-        const unsigned mh = tx_ballot(hit != 0u), mz = tx_ballot(z != 0u);
-        int pos = 0x7fffffff, nul = 0x7fffffff;
-        if (mh) { const int L = tx_ffs(mh) - 1; pos = base + 4 * L + tx_ffs(tx_shfl(hit, L)) - 1; }
+        const unsigned mz = tx_ballot(z != 0u);
+        int nul = 0x7fffffff;
         if (mz) { const int L = tx_ffs(mz) - 1; nul = base + 4 * L + ((tx_ffs(tx_shfl(z, L)) - 1) >> 3); }
-        if (pos < nul) return pos;                      // a match cannot contain a NUL: it lies in front of the first one
-        if (nul < base + 4 * kJudge) return -1;         // the string ends inside the judged positions
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            if (!((pm >> p) & 1u)) continue;  // warp-uniform
+            const int nw = (pats[p].plen + 3) >> 2;
+            unsigned hit = 0u;  // bit j: the pattern starts at o + j
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                bool ok = true;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k >= nw) continue;
+                    const unsigned win = j ? __funnelshift_r(v[k], v[k + 1], 8 * j) : v[k];
+                    ok = ok && ((win & pats[p].m[k]) == pats[p].w[k]);
+                }
+                hit |= (ok ? 1u : 0u) << j;
+            }
+            if (lane >= kJudge) hit = 0u;
+            const unsigned mh = tx_ballot(hit != 0u);
+            int at = 0x7fffffff;
+            if (mh) { const int L = tx_ffs(mh) - 1; at = base + 4 * L + tx_ffs(tx_shfl(hit, L)) - 1; }
+            if (at < nul) { res[p] = at; pm &= ~(1u << p); }                 // a match cannot contain a NUL: it lies in front of it
+            else if (nul < base + 4 * kJudge) pm &= ~(1u << p);              // the string ends inside the judged positions: absent
+        }
     }
-    return -1;
+    if (lane == 0) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) out[p * kStageRows] = (short)res[p];
+    }
 }
 #endif
 template <int NP>
@@ -243,21 +256,19 @@ SDQL_DEV void warp_text_resolve(const unsigned char* col, i64 row0, i64 n, int W
 #pragma unroll
     for (int p = 0; p < NP; ++p) reinterpret_cast<unsigned long long*>(pos + p * kStageRows)[lane] = ~0ull;  // this lane's 4 rows: -1
     tx_syncwarp();
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-        if (pats[p].plen > 16) continue;  // not resolved here (the caller keeps the per-lane search for it)
 #pragma unroll 1
-        for (int w = 0; w < kTextWords; ++w) {
-            unsigned m = mask[p * kTextWords + w];  // the same word in every lane
-            while (m) {
-                const int r = w * 32 + tx_ffs(m) - 1;
-                m &= m - 1u;
-                const unsigned char* s = col + (row0 + r) * (i64)W;
-                const int nw = (pats[p].plen + 3) >> 2;
-                const int f = nw == 1 ? warp_str_find<1>(s, W, pats[p]) : nw == 2 ? warp_str_find<2>(s, W, pats[p])
-                            : nw == 3 ? warp_str_find<3>(s, W, pats[p]) : warp_str_find<4>(s, W, pats[p]);
-                if (lane == 0) pos[p * kStageRows + r] = (short)f;
-            }
+    for (int w = 0; w < kTextWords; ++w) {
+        unsigned mp[NP], many = 0u;  // the same words in every lane
+#pragma unroll
+        for (int p = 0; p < NP; ++p) { mp[p] = pats[p].plen <= 16 ? mask[p * kTextWords + w] : 0u; many |= mp[p]; }
+        while (many) {
+            const int b = tx_ffs(many) - 1;
+            many &= many - 1u;
+            unsigned pm = 0u;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) pm |= ((mp[p] >> b) & 1u) << p;
+            const int r = w * 32 + b;
+            warp_row_find<NP>(col + (row0 + r) * (i64)W, W, pats, pm, pos + r);
         }
     }
     tx_syncwarp();

@@ -119,14 +119,20 @@ static long run_case(int W, long n, const char* const (&pats)[NP], unsigned seed
         for (auto& t : th) t.join();
         for (auto& m : want) m = 0;
         const long r1 = row0 + kStageRows < n ? row0 + kStageRows : n;
-        for (long r = row0; r < r1; ++r)
-            for (int i = 0; i < W; ++i) {
-                const size_t q = (size_t)r * W + i;
-                unsigned win = 0;
-                for (int j = 0; j < 4; ++j)
-                    if (q + j < bytes) win |= (unsigned)col[q + j] << (8 * j);
-                for (int p = 0; p < NP; ++p)
-                    if (win == pat4[p]) want[p * kTextWords + ((r - row0) >> 5)] |= 1u << ((r - row0) & 31);
+        const size_t run0 = (size_t)row0 * W, runb = r1 > row0 ? (size_t)(r1 - row0) * W : 0;
+        // scalar definition: a 16-byte chunk of the run with a hit position marks every row of the run it overlaps
+        for (size_t off = 0; off < runb; off += 16)
+            for (int p = 0; p < NP; ++p) {
+                bool hit = false;
+                for (size_t q = off; q < off + 16; ++q) {
+                    unsigned win = 0;
+                    for (int j = 0; j < 4; ++j)
+                        if (run0 + q + j < bytes) win |= (unsigned)col[run0 + q + j] << (8 * j);
+                    hit = hit || win == pat4[p];
+                }
+                if (!hit) continue;
+                const size_t last = off + 15 < runb ? off + 15 : runb - 1;
+                for (size_t r = off / W; r <= last / W; ++r) want[p * kTextWords + (r >> 5)] |= 1u << (r & 31);
             }
         for (int k = 0; k < NP * kTextWords; ++k)
             if (mask[k] != want[k]) { if (bad < 5) printf("MASK MISMATCH W=%d n=%ld row0=%ld word %d: got %08x want %08x\n", W, n, row0, k, mask[k], want[k]); ++bad; }
@@ -142,15 +148,19 @@ static long run_case(int W, long n, const char* const (&pats)[NP], unsigned seed
             for (int l = 0; l < 32; ++l)
                 th2.emplace_back([&, l] { t_lane = l; warp_text_scan_aligned<NP>(col, row0, n, W, pw, am.data()); });
             for (auto& t : th2) t.join();
-            for (size_t q = (size_t)row0 * W; q < (size_t)r1 * W; q += 4) {  // row0 * W is a multiple of 4
-                unsigned x = 0;
-                for (int j = 0; j < 4; ++j)
-                    if (q + j < bytes) x |= (unsigned)col[q + j] << (8 * j);
-                const long r = (long)(q / W);
-                for (int p = 0; p < NP; ++p)
-                    for (int o = 0; o < 4; ++o)
-                        if (x == pw[p][o]) aw[p * kTextWords + ((r - row0) >> 5)] |= 1u << ((r - row0) & 31);
-            }
+            for (size_t off = 0; off < runb; off += 16)  // row0 * W is a multiple of 16: chunks and words are aligned in the column
+                for (int p = 0; p < NP; ++p) {
+                    bool hit = false;
+                    for (size_t q = off; q < off + 16; q += 4) {
+                        unsigned x = 0;
+                        for (int j = 0; j < 4; ++j)
+                            if (run0 + q + j < bytes) x |= (unsigned)col[run0 + q + j] << (8 * j);
+                        for (int o = 0; o < 4; ++o) hit = hit || x == pw[p][o];
+                    }
+                    if (!hit) continue;
+                    const size_t last = off + 15 < runb ? off + 15 : runb - 1;
+                    for (size_t r = off / W; r <= last / W; ++r) aw[p * kTextWords + (r >> 5)] |= 1u << (r & 31);
+                }
             for (int k = 0; k < NP * kTextWords; ++k)
                 if (am[k] != aw[k]) { if (bad < 5) printf("ALIGNED MASK MISMATCH W=%d n=%ld row0=%ld word %d: got %08x want %08x\n", W, n, row0, k, am[k], aw[k]); ++bad; }
             for (long r = row0; r < r1; ++r)
