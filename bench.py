@@ -380,17 +380,24 @@ def main():
 
     def step():
         """one Q1 over the whole database: kernels + merge on every rank, result rows on the host of every rank"""
-        mod.execute(q, a, fetch=True)  # returns with the result rows in host memory (a.result.cols, malloc'ed by the module)
+        # returns with the result rows in host memory (a.result.cols, malloc'ed by the module); the module records a CUDA event
+        # around every kernel on its own stream (kernel_times): the roofline's launch durations come from the timed steps
+        mod.execute(q, a, fetch=True, kernel_times=True)
         if world > 1 and int(a.result_partial):  # rows emitted per owner rank: concatenated on every rank (not the case for Q1 / Q6)
             res = a.result
             n, nf = int(res.count), int(res.nfields)
             D.gather_rows([np.ctypeslib.as_array(res.cols[j], shape=(max(n, 1),))[:n] for j in range(nf)])
         mod.lib.sdqlb200_result_free(ct.byref(a.result))
+        if ksum is not None:
+            for k in range(int(a.launches)):
+                ksum[k] += a.kernel_ms[k]
         return int(a.launches)
 
     W = max(3, args.warmup)
+    ksum = None
     for _ in range(W):
         step()
+    ksum = [0.0] * 24  # per-kernel CUDA-event time summed over the timed steps
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -413,13 +420,14 @@ def main():
     # ---- rooflines: the kernels' own CUDA events (recorded around each launch inside the module) -------------------------
     peak, peak_src = peaks()
 
-    def kernel_roofline(qq, aa, mm):
-        kms = []
-        for _ in range(5):
-            mod.execute(qq, aa, fetch=True, kernel_times=True)
-            mod.lib.sdqlb200_result_free(ct.byref(aa.result))
-            kms.append([aa.kernel_ms[k] for k in range(int(aa.launches))])
-        kavg = np.mean(np.array(kms), axis=0)
+    def kernel_roofline(qq, aa, mm, kavg=None):
+        if kavg is None:  # not the timed query: its own steps
+            kms = []
+            for _ in range(args.steps):
+                mod.execute(qq, aa, fetch=True, kernel_times=True)
+                mod.lib.sdqlb200_result_free(ct.byref(aa.result))
+                kms.append([aa.kernel_ms[k] for k in range(int(aa.launches))])
+            kavg = np.mean(np.array(kms), axis=0)
         dom = int(np.argmax(kavg))
         b1, _ = scan_bytes_per_row(mm, "li")
         kbytes = rows * b1
@@ -428,7 +436,9 @@ def main():
                 "frac": ach / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": float(kavg[dom]),
                 "bytes_per_launch": kbytes, "rows_per_launch": rows, "bytes_per_row": b1,
                 "kernel_share_of_query": float(kavg[dom] / max(1e-9, float(aa.device_ms)))}
-    roofline = kernel_roofline(q, a, man)
+    roofline = kernel_roofline(q, a, man, np.array(ksum[:int(a.launches)]) / args.steps)
+    roofline["kernel_share_of_step"] = roofline["kernel_ms"] / ms_per_step
+    roofline["timing"] = "CUDA events around the launch on the module's stream, averaged over the %d timed steps" % args.steps
     prof = os.path.join(ROOT, "profiles", "r02_%s_traffic.json" % q)
     if os.path.exists(prof):  # dram__bytes per launch from the committed ncu --set full capture of the same kernel and size
         tr = json.load(open(prof))

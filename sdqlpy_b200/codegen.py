@@ -2272,8 +2272,8 @@ def render_query(q):
                 scan = "(unsigned long long)c.n_%s * %dull" % (K.src[1], max(4, pb))
             else:
                 scan = "(unsigned long long)c.%s.cap * 12ull" % K.src[1].name
-            L.append("    const bool cnt_%s = (%s) >= sdqlhost::count_min_bytes() && (%s) >= sdqlhost::count_min_ratio() * (%s);" %
-                     (K.name, tot, tot, scan))
+            L.append("    const bool cnt_%s = (%s) >= sdqlhost::count_min_bytes() && ((%s) >= sdqlhost::count_min_ratio() * (%s) || (%s) >= sdqlhost::count_big_bytes());" %
+                     (K.name, tot, tot, scan, tot))
             # tables merged across ranks are planned for the GLOBAL row count (600 M lineitems -> 2^30 slots, whatever the
             # predicates let through): they are counted whenever that worst case is big -- a rank-independent rule -- and the
             # ranks' counts are summed, so every rank re-plans the table alike (Q20 on 2 GPUs: 16.9 ms with the worst-case plan)

@@ -204,6 +204,14 @@ static inline unsigned long long count_min_ratio() {
     if (v < 0) { const char* e = getenv("SDQLB200_COUNT_MIN_RATIO"); v = e ? atoll(e) : 4; if (v < 0) v = 0; }
     return (unsigned long long)v;
 }
+// ... or is simply huge: initialising and then randomly touching several GB costs more than a second pass over the
+// predicate columns whatever the ratio (Q12 at SF100: 12.6 GB direct table for 3 M entries, 8.3 ms; counted: 4.7 ms;
+// lowering the ratio for everybody instead cost Q7 / Q9 / Q20 0.3-0.9 ms each, profiles/r02_visit8)
+static inline unsigned long long count_big_bytes() {
+    static long long v = -1;
+    if (v < 0) { const char* e = getenv("SDQLB200_COUNT_BIG_BYTES"); v = e ? atoll(e) : (4ll << 30); if (v < 0) v = 0; }
+    return (unsigned long long)v;
+}
 static inline bool debug() {
     static const bool d = getenv("SDQLB200_DEBUG") && getenv("SDQLB200_DEBUG")[0] == '1';
     return d;
