@@ -221,10 +221,17 @@ SDQL_DEV bool tbl_maybe(const Tbl& t, u64 key) {
     const u64 b = t.bmod ? key % t.bmod : key;
     return (ld1(t.bits + (b >> 5)) >> (unsigned)(b & 31)) & 1u;
 }
-// dictionary-valued entry d[k] of a table keyed by (k, x): may any (k, x) be present?  outer = packed k, x in [0, rng)
-SDQL_DEV bool tbl_maybe_outer(const Tbl& t, u64 outer, i64 rng, i64 mul) {
+// the same with the packed first key part at hand (p0 == key % bmod): no 64-bit modulo
+SDQL_DEV bool tbl_maybe(const Tbl& t, u64 key, u64 p0) {
     if (!t.bits) return true;
-    if (t.bmod) return tbl_maybe(t, outer);
+    stat(kStBitTests);
+    const u64 b = t.bmod ? p0 : key;
+    return (ld1(t.bits + (b >> 5)) >> (unsigned)(b & 31)) & 1u;
+}
+// dictionary-valued entry d[k] of a table keyed by (k, x): may any (k, x) be present?  outer = packed k, x in [0, rng)
+SDQL_DEV bool tbl_maybe_outer(const Tbl& t, u64 outer, i64 rng, i64 mul, u64 p0) {
+    if (!t.bits) return true;
+    if (t.bmod) return tbl_maybe(t, outer, p0);
     for (i64 x = 0; x < rng; ++x)
         if (tbl_maybe(t, outer + (u64)x * (u64)mul)) return true;
     return false;
@@ -269,7 +276,13 @@ SDQL_DEV int tbl_probe(const Tbl& t, u64 key) {
 #endif
 }
 
-// -> slot or -1.  `ok` = every key part was inside the table's packing range.
+// -> slot or -1.  `ok` = every key part was inside the table's packing range.  p0: the packed first key part.
+SDQL_DEV int tbl_find(const Tbl& t, u64 key, bool ok, u64 p0) {
+    if (!ok || !tbl_maybe(t, key, p0)) return -1;
+    stat(kStFinds);
+    if (t.direct) { stat(kStFindSlots); return ld1(t.rep + key) != -1 ? (int)key : -1; }  // -2 = present, owned by another rank
+    return tbl_probe(t, key);
+}
 SDQL_DEV int tbl_find(const Tbl& t, u64 key, bool ok) {
     if (!ok || !tbl_maybe(t, key)) return -1;
     stat(kStFinds);
