@@ -2374,6 +2374,10 @@ def render_query(q):
                 L.append("                if (sdqlhost::debug()) fprintf(stderr, \"[sdqlb200] %s: %%llu rows reach the build of %s -> %%s, %%lld slots%%s\\n\", h_cnt, c.%s.direct ? \"direct\" : \"hash\", (long long)c.%s.cap, rp_ ? \" (re-planned)\" : \"\");" % (K.name, t.name, t.name, t.name))
                 for j, (_, ct) in enumerate(t.fields):
                     L.append("                c.%s_a%d = (%s*)ag[%d];" % (t.name, j, CT[ct], j))
+                if getattr(t, "want_bits", False):
+                    # the new layout brought the presence filter back: still none for a merged table (the merge adds the
+                    # other ranks' keys behind the bitmap's back -- probes for them would miss: Q20 on 2 GPUs lost 28 % of its rows)
+                    L.append("                if (merged_) c.%s.bits = nullptr;" % t.name)
                 L.append("            }")
             L.append("        }")
             for t in owned[K]:

@@ -27,14 +27,15 @@ def _worker(rank, world, so, port, queries, out):
     runtime.set_backend(emu.EmuBackend())
     runtime.set_distributed(runtime.DistConfig(partitioned=("li", "ord")))
     mod = runtime.CompiledModule(so)
-    g = TPCH(0.01)
+    sf = float(os.environ.get("SDQL_TEST_SF", "0.01"))
+    g = TPCH(sf)
     half = g.O // world
     orng = (rank * half, (rank + 1) * half if rank < world - 1 else g.O)
     tabs = {}
     for t in SCHEMAS:
         cols = g.columns(t, None, orng) if t in ("lineitem", "orders") else g.columns(t)
         tabs[t] = [cols.get(c) for c, _ in SCHEMAS[t]]
-    gold = golden(0.01)
+    gold = golden(sf)
     bad = []
     for q in queries:
         try:
@@ -96,6 +97,9 @@ def test_world2_merged_tables_are_counted_and_replanned_alike(emu_so, tmp_path, 
     collectives would not match) -- results must not change"""
     monkeypatch.setenv("SDQLB200_COUNT_MIN_BYTES", "0")
     monkeypatch.setenv("SDQLB200_COUNT_MIN_RATIO", "0")
+    # SF0.05: Q20's merged <partkey, suppkey> table has enough entries on both ranks for a stale presence filter to show (on
+    # 2 B200s it returned 12 of 14 rows when the re-planned layout brought the filter back)
+    monkeypatch.setenv("SDQL_TEST_SF", "0.05")
     out = str(tmp_path / "res.txt")
     mp.spawn(_worker, args=(2, emu_so, 29737, SUPPORTED, out), nprocs=2, join=True)
     bad, merges, tmerges = open(out).read().split("\n")
