@@ -2370,7 +2370,7 @@ def render_query(q):
                 nf = len(t.fields)
                 L.append("            {")
                 L.append("                void* ag[%d] = {%s};" % (max(1, nf), ", ".join("c.%s_a%d" % (t.name, j) for j in range(nf)) or "nullptr"))
-                L.append("                const bool rp_ = sdqlhost::replan_table(&c.%s, (char*)a->workspace, &tr[%d], (long long)h_cnt, ag);" % (t.name, t.index))
+                L.append("                const bool rp_ = sdqlhost::replan_table(&c.%s, (char*)a->workspace, &tr[%d], (long long)h_cnt, ag, merged_ ? 4 : 64);" % (t.name, t.index))
                 L.append("                if (sdqlhost::debug()) fprintf(stderr, \"[sdqlb200] %s: %%llu rows reach the build of %s -> %%s, %%lld slots%%s\\n\", h_cnt, c.%s.direct ? \"direct\" : \"hash\", (long long)c.%s.cap, rp_ ? \" (re-planned)\" : \"\");" % (K.name, t.name, t.name, t.name))
                 for j, (_, ct) in enumerate(t.fields):
                     L.append("                c.%s_a%d = (%s*)ag[%d];" % (t.name, j, CT[ct], j))

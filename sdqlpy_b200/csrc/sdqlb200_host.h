@@ -161,12 +161,14 @@ static inline bool size_table(sdqlrt::Tbl* t, int nparts, const long long* mn, c
 
 // Right-size a table once the number of rows that reach its build is known (cardinality pass): same region, smaller
 // (cache-resident) arrays.  Keeps the worst-case plan when the new one would not fit the reservation.
-static inline bool replan_table(sdqlrt::Tbl* t, char* base, TblRegion* r, long long rows, void** aggs) {
+static inline bool replan_table(sdqlrt::Tbl* t, char* base, TblRegion* r, long long rows, void** aggs, long long sparse = 64) {
     int direct;
     long long cap;
     // with the true cardinality known, a dense array stays the better table down to one key per 64 slots: sorted
-    // builds and probes stream through it, while a hash table of millions of keys is built with random CAS traffic
-    plan_table(r->dom, rows, &direct, &cap, 64);
+    // builds and probes stream through it, while a hash table of millions of keys is built with random CAS traffic.
+    // (A table that is merged across ranks passes sparse = 4: a dense table is merged by all-reducing the WHOLE array --
+    // Q17's 20 M-slot table for 20 K parts moved 400 MB per merge -- a hashed one by shuffling its entries.)
+    plan_table(r->dom, rows, &direct, &cap, sparse);
     if (table_bytes(direct, cap, r->nf) + bits_bytes(r->bdom) > r->len) return false;
     if (direct == t->direct && cap == t->cap) return false;
     t->direct = direct;

@@ -15,7 +15,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
     sys.path.insert(0, p)
 
 import numpy as np  # noqa: E402
@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--check", default="none")
     ap.add_argument("--out", default=None)
     ap.add_argument("--device-gen", action="store_true", help="lineitem / orders partitions generated on the GPU")
+    ap.add_argument("--trace", action="store_true", help="one extra run per query with SDQLB200_F_TRACE: rank 0 reports the "
+                    "wall-clock time of every step of the host driver (kernels, table initialisation, merges)")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -101,6 +103,12 @@ def main():
                "gen_s": round(gen_s, 1), "result_rows": len(rows) if isinstance(rows, list) else 1,
                "workspace_MB": round(mod.last.workspace_bytes / 1e6, 1), "merges_total": mod.merges,
                "table_merges_total": mod.table_merges, "p2p_merges_total": mod.p2p_merges}
+        if a.trace:  # every rank runs it (the merges are collective); rank 0 keeps the lines
+            from run_tpch import traced_run
+            args_, keep_ = mod.prepare(q, db)
+            steps = traced_run(mod, q, args_)
+            row["trace_ms"] = [[s_, round(ms_, 4)] for s_, ms_ in steps if ms_ >= 0.02]
+            del args_, keep_
         if rank == 0 and a.check != "none":
             full = TPCH(a.sf)
             t0 = time.time()
