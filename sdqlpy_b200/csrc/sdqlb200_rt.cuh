@@ -241,15 +241,16 @@ SDQL_DEV u64 hash64(u64 x) {  // splitmix64 finaliser
     return x;
 }
 
-// Probe of a hashed table (open addressing, linear probing).  SDQLB200_PROBE_SECTOR: the probe examines the whole 32-byte
-// sector the home slot lies in -- four 8-byte keys, two 128-bit loads -- per memory round trip: the sector is what a random
-// 8-byte read moves anyway, and a probe chain of up to four slots inside it resolves without a second dependent load (what
-// a 4-lane cooperative group per key would achieve, without giving up 3 of 4 lanes to it).  Tables have >= 1024 slots
-// (power of two), so a group of four never wraps.
+// Probe of a hashed table (open addressing, linear probing).  The probe examines the whole 32-byte sector the home slot
+// lies in -- four 8-byte keys, two 128-bit loads -- per memory round trip: the sector is what a random 8-byte read moves
+// anyway, and a probe chain of up to four slots inside it resolves without a second dependent load (what a 4-lane
+// cooperative group per key would achieve, without giving up 3 of 4 lanes to it).  Tables have >= 1024 slots (power of
+// two), so a group of four never wraps.  B200, SF100 (profiles/r02_visit10/r02_v10_ab_probe_sf100.json): q9_k5 6.85 ->
+// 6.46 ms, q20_k3 3.47 -> 3.17 ms, Q2 0.746 -> 0.717 ms against one slot per step (-DSDQLB200_PROBE_SLOT keeps that).
 SDQL_DEV int tbl_probe(const Tbl& t, u64 key) {
     const u64 m = (u64)t.cap - 1;
     u64 h = hash64(key) & m;
-#if defined(SDQLB200_PROBE_SECTOR) && !defined(SDQLB200_EMU)
+#if !defined(SDQLB200_PROBE_SLOT) && !defined(SDQLB200_EMU)
     for (;;) {
         stat(kStFindSlots);
         const u64 base = h & ~3ull;

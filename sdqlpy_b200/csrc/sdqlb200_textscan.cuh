@@ -21,9 +21,10 @@ SDQL_DEV unsigned pat4_of(const char* pat) {  // first four characters as one li
            ((unsigned)(unsigned char)pat[2] << 16) | ((unsigned)(unsigned char)pat[3] << 24);
 }
 #ifndef SDQLB200_EMU
-// 16 bytes at src + off as four little-endian words; bytes at or behind `total` read as zero (no access past the column)
-SDQL_DEV void text_load16(const unsigned char* src, size_t off, size_t total, unsigned (&w)[4]) {
-    if (off + 16 <= total) {
+// 16 bytes at src + off as four little-endian words; bytes at or behind `total` read as zero (no access past the column).
+// Offsets are run-local (a run is at most kStageRows rows: 32-bit arithmetic in the scan loop).
+SDQL_DEV void text_load16(const unsigned char* src, unsigned off, unsigned total, unsigned (&w)[4]) {
+    if (off + 16u <= total) {
         tx_ldnc16(src + off, w);
     } else {
         w[0] = w[1] = w[2] = w[3] = 0u;
@@ -32,21 +33,26 @@ SDQL_DEV void text_load16(const unsigned char* src, size_t off, size_t total, un
             if (off + j < total) w[j >> 2] |= (unsigned)ld1(src + off + j) << (8 * (j & 3));
     }
 }
-SDQL_DEV unsigned text_load4(const unsigned char* src, size_t off, size_t total) {
-    if (off + 4 <= total) return ld1((const unsigned*)(src + off));
+SDQL_DEV unsigned text_load4(const unsigned char* src, unsigned off, unsigned total) {
+    if (off + 4u <= total) return ld1((const unsigned*)(src + off));
     unsigned v = 0u;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
         if (off + j < total) v |= (unsigned)ld1(src + off + j) << (8 * j);
     return v;
 }
+// readable bytes from the run's start, clamped to what the scan can touch (its own bytes + the 3 chunks it requests ahead)
+SDQL_DEV unsigned text_total(i64 n, i64 row0, int W, unsigned bytes) {
+    const size_t t = (size_t)(n - row0) * (size_t)W;
+    return t > (size_t)bytes + 4096u ? bytes + 4096u : (unsigned)t;
+}
 #endif
 #ifndef SDQLB200_EMU
 // marks the rows of the run that the 16-byte chunk at byte `off` overlaps (two at most when W >= 16)
-SDQL_DEV void text_mark_chunk(unsigned* mask, size_t off, size_t bytes, int W) {
-    const unsigned r0 = (unsigned)(off / (size_t)W);
-    const size_t last = off + 15 < bytes ? off + 15 : bytes - 1;
-    const unsigned r1 = (unsigned)(last / (size_t)W);
+SDQL_DEV void text_mark_chunk(unsigned* mask, unsigned off, unsigned bytes, int W) {
+    const unsigned r0 = off / (unsigned)W;
+    const unsigned last = off + 15u < bytes ? off + 15u : bytes - 1u;
+    const unsigned r1 = last / (unsigned)W;
     for (unsigned r = r0; r <= r1; ++r) tx_atomic_or(mask + (r >> 5), 1u << (r & 31u));
 }
 #endif
@@ -60,22 +66,27 @@ SDQL_DEV void warp_text_scan(const unsigned char* col, i64 row0, i64 n, int W, c
     if (lane < NP * kTextWords) mask[lane] = 0u;
     tx_syncwarp();
     if (r1 <= row0) return;  // the same decision in every lane
-    const size_t bytes = (size_t)(r1 - row0) * (size_t)W;       // this run
-    const size_t total = (size_t)(n - row0) * (size_t)W;        // readable bytes from the run's start to the column's end
+    const unsigned bytes = (unsigned)(r1 - row0) * (unsigned)W;  // this run
+    const unsigned total = text_total(n, row0, W, bytes);        // readable bytes from the run's start (clamped)
     const unsigned char* src = col + row0 * W;                   // 16-byte aligned: row0 is a multiple of 128, the base of 256
-    const size_t nv = (bytes + 15) >> 4;
-    // software pipeline: the next step's chunk is requested before this one is examined.  The three bytes behind a
-    // chunk are the start of the next lane's chunk (one shuffle); the last lane fetches its own (a 4-byte load out of
-    // the line the next step's first lane reads anyway).
-    unsigned nx[4], nx4 = 0u;
-    text_load16(src, (size_t)lane << 4, total, nx);
-    if (lane == 31) nx4 = text_load4(src, ((size_t)lane << 4) + 16, total);
-    for (size_t kb = 0; kb < nv; kb += 32) {
-        const size_t off = (kb + lane) << 4;
+    const unsigned nv = (bytes + 15u) >> 4;
+    // software pipeline: two steps' chunks are in flight while one is examined (one was not enough to cover the HBM latency:
+    // 23 % of q13_k0's stall samples sat on the chunk's first use).  The three bytes behind a chunk are the start of the next
+    // lane's chunk (one shuffle); the last lane fetches its own (a 4-byte load out of the line the next step's first lane
+    // reads anyway).
+    unsigned nx[4], ny[4], nx4 = 0u, ny4 = 0u;
+    text_load16(src, (unsigned)lane << 4, total, nx);
+    text_load16(src, ((unsigned)lane << 4) + 512u, total, ny);
+    if (lane == 31) { nx4 = text_load4(src, ((unsigned)lane << 4) + 16u, total); ny4 = text_load4(src, ((unsigned)lane << 4) + 528u, total); }
+    for (unsigned kb = 0; kb < nv; kb += 32) {
+        const unsigned off = (kb + lane) << 4;
         unsigned w[5] = {nx[0], nx[1], nx[2], nx[3], nx4};
-        if (kb + 32 < nv) {
-            text_load16(src, off + 512, total, nx);
-            if (lane == 31) nx4 = text_load4(src, off + 528, total);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nx[j] = ny[j];
+        nx4 = ny4;
+        if (kb + 64 < nv) {
+            text_load16(src, off + 1024u, total, ny);
+            if (lane == 31) ny4 = text_load4(src, off + 1040u, total);
         }
         const unsigned dn = tx_shfl_down(w[0], 1);
         if (lane != 31) w[4] = dn;
@@ -134,16 +145,19 @@ SDQL_DEV void warp_text_scan_aligned(const unsigned char* col, i64 row0, i64 n, 
     if (lane < NP * kTextWords) mask[lane] = 0u;
     tx_syncwarp();
     if (r1 <= row0) return;
-    const size_t bytes = (size_t)(r1 - row0) * (size_t)W;
-    const size_t total = (size_t)(n - row0) * (size_t)W;
+    const unsigned bytes = (unsigned)(r1 - row0) * (unsigned)W;
+    const unsigned total = text_total(n, row0, W, bytes);
     const unsigned char* src = col + row0 * W;
-    const size_t nv = (bytes + 15) >> 4;
-    unsigned nx[4];
-    text_load16(src, (size_t)lane << 4, total, nx);
-    for (size_t kb = 0; kb < nv; kb += 32) {
-        const size_t off = (kb + lane) << 4;
+    const unsigned nv = (bytes + 15u) >> 4;
+    unsigned nx[4], ny[4];  // two steps' chunks in flight
+    text_load16(src, (unsigned)lane << 4, total, nx);
+    text_load16(src, ((unsigned)lane << 4) + 512u, total, ny);
+    for (unsigned kb = 0; kb < nv; kb += 32) {
+        const unsigned off = (kb + lane) << 4;
         const unsigned w[4] = {nx[0], nx[1], nx[2], nx[3]};
-        if (kb + 32 < nv) text_load16(src, off + 512, total, nx);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nx[j] = ny[j];
+        if (kb + 64 < nv) text_load16(src, off + 1024u, total, ny);
         if (off >= bytes) continue;
         bool hit[NP];
 #pragma unroll
