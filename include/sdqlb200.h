@@ -22,9 +22,15 @@ enum { SDQLB200_I32 = 0, SDQLB200_F64 = 1, SDQLB200_CODE = 2, SDQLB200_BYTES = 3
 enum { SDQLB200_OK = 0, SDQLB200_E_WORKSPACE = -1, SDQLB200_E_CUDA = -2, SDQLB200_E_ARG = -3, SDQLB200_E_NOQUERY = -4 };
 enum { SDQLB200_F_NOFETCH = 1, SDQLB200_F_KERNEL_TIMES = 2, SDQLB200_F_TRACE = 4 /* per-step wall-clock times on stderr */ };
 enum { SDQLB200_COL_PARTKEY = 1 };                       /* sdqlb200_col.flags: the relation is range partitioned on this column */
-enum { SDQLB200_SUM_F64 = 0, SDQLB200_SUM_I64 = 1, SDQLB200_MIN_I32 = 2, SDQLB200_MERGE_TABLE = 3 }; /* merge ops */
+enum { SDQLB200_SUM_F64 = 0, SDQLB200_SUM_I64 = 1, SDQLB200_MIN_I32 = 2, SDQLB200_MERGE_TABLE = 3, SDQLB200_MERGE_DIRECT = 4 }; /* merge ops */
 /* multi-GPU: called (stream ordered) after a kernel over a partitioned relation for every partial buffer that has to
  * be combined across ranks.  SUM / MIN: the callee all-reduces `count` elements at workspace + offset in place (NCCL).
+ * MERGE_DIRECT: `workspace_offset` carries a HOST pointer to a sdqlb200_table with keys == NULL: a direct-indexed partial
+ * dictionary of `cap` slots (rep[slot] >= 0: present on this rank).  The callee may merge it SPARSELY -- the ranks exchange
+ * their occupied slots, every rank adds the others' fields into its own arrays and marks the entries a lower rank also holds
+ * (or that it does not hold itself) rep = -2 -- and return 0, or decline with +1 when the table is dense enough that
+ * all-reducing the whole arrays is cheaper (the module then does that with MIN_I32 + SUM); the decision is taken from
+ * all-gathered counts, alike on every rank.  Q17's 20 M-slot table holds 20 K parts: 400 MB per dense merge.
  * MERGE_TABLE: `workspace_offset` carries a HOST pointer to a sdqlb200_table describing a hashed partial dictionary;
  * the callee merges it across ranks with the sdqlb200_table_* helpers below (hash all-to-all, combine at the
  * destination, all-gather, write back).  The reference's counterpart is the serial AddMap merge of thread-local

@@ -57,6 +57,9 @@ int sdqlb200_comm_allreduce(sdqlb200_comm* c, void* d_buf, uint64_t count, int32
 /* SDQLB200_MERGE_TABLE: all-reduce of a hashed partial dictionary.  Synchronises the stream twice (run lengths).
  * Fails on EVERY rank alike when the union of the keys does not fit t->cap / 2. */
 int sdqlb200_comm_merge_table(sdqlb200_comm* c, const sdqlb200_table* t, void* stream);
+/* SDQLB200_MERGE_DIRECT: sparse merge of a direct-indexed partial dictionary (t->keys == NULL): 0 = merged, 1 = declined
+ * (the table is dense enough for an all-reduce of its arrays, alike on every rank), < 0 = error.  Synchronises the stream once. */
+int sdqlb200_comm_merge_direct(sdqlb200_comm* c, const sdqlb200_table* t, void* stream);
 /* concatenation of the ranks' result rows: every rank contributes `count` rows of `nfields` 8-byte columns (column j at
  * cols[j], in host OR device memory -- the copy direction is inferred from the pointer); on return h_total = rows of all ranks and h_out[j] (malloc'ed here, caller frees) holds
  * column j of all ranks in rank order.  Synchronises the stream. */

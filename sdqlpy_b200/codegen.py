@@ -1334,6 +1334,9 @@ class Query:
                 and K is not None and K.src == ("rel", s.arg) and len(pattern) >= 4 and "\0" not in pattern):
             return None
         idx = self.input(s.arg, s.col, "bytes")
+        if not hasattr(K, "str_scan"):
+            K.str_scan = OrderedDict()
+        K.str_scan[s.col] = s.width  # the manifest's scanned string bytes (roofline accounting)
         w, pats = K.text_cols.setdefault(idx, [s.width, []])
         if pattern not in pats:
             if len(pats) >= 8:
@@ -2024,7 +2027,7 @@ def merge_code(q, K):
         L.append("                if (a->merge(a->merge_ctx, (unsigned long long)(uintptr_t)&td, 0, SDQLB200_MERGE_TABLE)) return sdqlhost::fail(SDQLB200_E_ARG, \"%s: merging hashed table %s across ranks failed\");" % (q.name, t.name))
         nf64 = sum(1 for _, ct in t.fields if ct == "f64")
         words = 1 + nf64 + 2 * (len(t.fields) - nf64)
-        L.append("            } else if (c.%s.cap <= sdqlrt::kFusedMergeMaxSlots) {  // small table: presence + all fields in ONE all-reduce" % t.name)
+        L.append("            } else if (c.%s.cap <= sdqlhost::fused_merge_max()) {  // small table: presence + all fields in ONE all-reduce" % t.name)
         L.append("                sdqlrt::TblIO io; memset(&io, 0, sizeof io);")
         L.append("                io.rep = c.%s.rep; io.cap = c.%s.cap; io.nf = %d; io.f64_mask = %du;" %
                  (t.name, t.name, len(t.fields), sum(1 << j for j, (_, ct) in enumerate(t.fields) if ct == "f64")))
@@ -2036,6 +2039,17 @@ def merge_code(q, K):
                  (off % ("mg_%s" % t.name), t.name, words))
         L.append("                SDQL_LAUNCH(sdqlrt::k_merge_unpack, og, sdqlrt::kBlock, 0, st, io, a->rank, mg_%s);" % t.name)
         L.append("            } else {")
+        L.append("            int sp_ = 1;  // large direct table: sparse merge of its occupied slots when few are (SDQLB200_MERGE_DIRECT)")
+        L.append("            {")
+        L.append("                sdqlb200_table td; memset(&td, 0, sizeof td);")
+        L.append("                td.keys = nullptr; td.rep = c.%s.rep; td.cap = c.%s.cap; td.nfields = %d; td.f64_mask = %du;" %
+                 (t.name, t.name, len(t.fields), sum(1 << j for j, (_, ct) in enumerate(t.fields) if ct == "f64")))
+        for j in range(len(t.fields)):
+            L.append("                td.agg[%d] = c.%s_a%d;" % (j, t.name, j))
+        L.append("                sp_ = a->merge(a->merge_ctx, (unsigned long long)(uintptr_t)&td, 0, SDQLB200_MERGE_DIRECT);")
+        L.append("                if (sp_ != 0 && sp_ != 1) return sdqlhost::fail(SDQLB200_E_ARG, \"%s: merging direct table %s across ranks failed\");" % (q.name, t.name))
+        L.append("            }")
+        L.append("            if (sp_ == 1) {")
         L.append("            const int og = sdqlhost::grid_for(c.%s.cap, 8, sms);" % t.name)
         L.append("            SDQL_LAUNCH(sdqlrt::k_owner_encode, og, sdqlrt::kBlock, 0, st, c.%s.rep, own_%s, c.%s.cap, a->rank);" % (t.name, t.name, t.name))
         L.append("            if (a->merge(a->merge_ctx, %s, (unsigned long long)c.%s.cap, SDQLB200_MIN_I32)) return sdqlhost::fail(SDQLB200_E_ARG, \"merge callback failed\");" % (off % ("own_%s" % t.name), t.name))
@@ -2050,6 +2064,7 @@ def merge_code(q, K):
             L.append("            if (a->merge(a->merge_ctx, %s, %s, %s)) return sdqlhost::fail(SDQLB200_E_ARG, \"merge callback failed\");" %
                      (off % ("c.%s_a%d" % (t.name, j)), cnt, "SDQLB200_SUM_F64" if ct == "f64" else "SDQLB200_SUM_I64"))
             j = k + 1
+        L.append("            }")
         L.append("            }")
         consumers = [K2 for K2 in q.kernels if K2.src == ("tbl", t)]
         if consumers and all(iterates_without_rep(K2) for K2 in consumers):
@@ -2175,7 +2190,7 @@ def render_query(q):
             L.append("    double* mg_%s = a->merge ? ar.alloc<double>(65536ll * %d) : nullptr;" % (t.name, 1 + nf64 + 2 * (len(t.fields) - nf64)))
             continue
         L.append("    int* own_%s = a->merge ? ar.alloc<int>(c.%s.cap) : nullptr;" % (t.name, t.name))
-        L.append("    double* mg_%s = (a->merge && c.%s.cap <= sdqlrt::kFusedMergeMaxSlots) ? ar.alloc<double>(c.%s.cap * %d) : nullptr;" %
+        L.append("    double* mg_%s = (a->merge && c.%s.cap <= sdqlhost::fused_merge_max()) ? ar.alloc<double>(c.%s.cap * %d) : nullptr;" %
                  (t.name, t.name, t.name, 1 + nf64 + 2 * (len(t.fields) - nf64)))
     L.append("    const unsigned long long tail_off = ar.used;  // scalars, counters, partials: zeroed before every run")
     L.append("    c.sc = ar.alloc<double>(%d); c.cnt = ar.alloc<unsigned>(%d); c.tcount = ar.alloc<unsigned long long>(%d);" %
@@ -2273,15 +2288,22 @@ def render_query(q):
             # predicate columns a second time
             if K.src[0] == "rel":
                 pb = sum({"i32": 4, "f64": 8, "code": 1}[rep] for (_, rep) in (K.pred_cols or ())) + sum(K.byte_cols.values())
+                pb += sum(w_ for w_, _ in K.text_cols.values())  # the warp text scan streams the whole string column
                 scan = "(unsigned long long)c.n_%s * %dull" % (K.src[1], max(4, pb))
+                ai_ = q.args.index(K.src[1])
+                scan_g = "(unsigned long long)((a->nrows_global && ((a->part_mask >> %d) & 1u)) ? a->nrows_global[%d] : c.n_%s) * %dull" % (
+                    ai_, ai_, K.src[1], max(4, pb))
             else:
                 scan = "(unsigned long long)c.%s.cap * 12ull" % K.src[1].name
+                scan_g = "(~0ull >> 4)"  # the source table's size may differ between ranks: only the absolute rule below
             L.append("    const bool cnt_%s = (%s) >= sdqlhost::count_min_bytes() && ((%s) >= sdqlhost::count_min_ratio() * (%s) || (%s) >= sdqlhost::count_big_bytes());" %
                      (K.name, tot, tot, scan, tot))
             # tables merged across ranks are planned for the GLOBAL row count (600 M lineitems -> 2^30 slots, whatever the
-            # predicates let through): they are counted whenever that worst case is big -- a rank-independent rule -- and the
-            # ranks' counts are summed, so every rank re-plans the table alike (Q20 on 2 GPUs: 16.9 ms with the worst-case plan)
-            L.append("    const bool cntm_%s = (%s) >= sdqlhost::count_min_bytes();" % (K.name, tot))
+            # predicates let through): the same rule decides from rank-independent numbers (global rows) whether to count, and
+            # the ranks' counts are summed, so every rank re-plans the table alike (Q20 on 2 GPUs: 16.9 ms with the worst-case
+            # plan, 2.8 ms counted).  Counting everything big lost: q13_k0's second text scan cost 3 ms for nothing (visit 11)
+            L.append("    const bool cntm_%s = (%s) >= sdqlhost::count_min_bytes() && ((%s) >= sdqlhost::count_min_ratio() * (%s) || (%s) >= sdqlhost::count_big_bytes());" %
+                     (K.name, tot, tot, scan_g, tot))
             L.append("    const bool late_%s = cnt_%s || (a->merge != nullptr && cntm_%s);  // its tables are initialised right before it" %
                      (K.name, K.name, K.name))
     L.append("    g_trace = (a->flags & SDQLB200_F_TRACE) != 0 || sdqlhost::debug();")

@@ -402,6 +402,45 @@ int sdqlb200_comm_merge_table(sdqlb200_comm* c, const sdqlb200_table* t, void* s
     return rc;
 }
 
+// SDQLB200_MERGE_DIRECT: -> 0 merged sparsely, 1 declined (dense: the caller all-reduces the arrays), < 0 error
+int sdqlb200_comm_merge_direct(sdqlb200_comm* c, const sdqlb200_table* t, void* stream) {
+    if (!t || t->keys || !t->rep || t->cap < 1 || t->nfields < 0 || t->nfields > 16) return COMM_FAIL("comm_merge_direct: bad table descriptor");
+    if (c->world == 1) return 0;
+    sdqlrt::TblIO io;
+    memset(&io, 0, sizeof io);
+    io.rep = t->rep; io.cap = t->cap; io.nf = t->nfields; io.f64_mask = t->f64_mask;
+    for (int j = 0; j < t->nfields; ++j) io.agg[j] = (u64*)t->agg[j];
+    cudaStream_t st = (cudaStream_t)stream;
+    const int W = c->world, R = 2 + io.nf, sms = 148;
+    u64* d_cnt = c->d_scratch;        // [1] my occupied slots
+    u64* d_all = c->d_scratch + 16;   // [W]
+    u64* d_cur = c->d_scratch + 32;   // pack cursor
+    SDQL_CUDA(cudaMemsetAsync(c->d_scratch, 0, 512, st));
+    const int g = sdqlhost::grid_for(io.cap, 8, sms);
+    sdqlrt::k_dtbl_count<<<g, sdqlrt::kBlock, 0, st>>>(io, d_cnt);
+    SDQL_NCCL(g_nccl.AllGather(d_cnt, d_all, 1, ncclUint64, c->nccl, st));
+    SDQL_CUDA(cudaMemcpyAsync(c->h_scratch, d_all, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
+    SDQL_CUDA(cudaStreamSynchronize(st));
+    u64 m[kMaxWorld], moff[kMaxWorld], total = 0;
+    for (int r = 0; r < W; ++r) { m[r] = c->h_scratch[r]; moff[r] = total; total += m[r]; }
+    // the same numbers on every rank: all decline or none does.  Dense moves the whole arrays through an all-reduce
+    // (rep as int32 MIN + nf 8-byte SUMs), sparse the occupied slots of every rank to every rank + one atomic per field
+    const double dense = (double)io.cap * (4.0 + 8.0 * io.nf), sparse = (double)total * 8.0 * R;
+    if (2.0 * sparse >= dense) return 1;
+    i64* d_allrec = nullptr;
+    SDQL_CUDA(cudaMallocAsync((void**)&d_allrec, (total + 1) * R * 8, st));
+    if (m[c->rank]) sdqlrt::k_dtbl_pack<<<g, sdqlrt::kBlock, 0, st>>>(io, c->rank, d_cur, d_allrec + moff[c->rank] * R);
+    SDQL_NCCL(g_nccl.GroupStart());
+    for (int r = 0; r < W; ++r)
+        if (m[r]) SDQL_NCCL(g_nccl.Broadcast(d_allrec + moff[r] * R, d_allrec + moff[r] * R, m[r] * R, ncclInt64, r, c->nccl, st));
+    SDQL_NCCL(g_nccl.GroupEnd());
+    if (total) sdqlrt::k_dtbl_absorb<<<sdqlhost::grid_for((i64)total, 8, sms), sdqlrt::kBlock, 0, st>>>(
+        io, d_allrec, (i64)total, (i64)moff[c->rank], (i64)(moff[c->rank] + m[c->rank]), c->rank);
+    SDQL_CUDA(cudaGetLastError());
+    SDQL_CUDA(cudaFreeAsync(d_allrec, st));
+    return 0;
+}
+
 int sdqlb200_comm_gather_rows(sdqlb200_comm* c, const int64_t* const* cols, int32_t nfields, int64_t count,
                               int64_t** h_out, int64_t* h_total, void* stream) {
     if (nfields < 0 || nfields > 32 || count < 0) return COMM_FAIL("comm_gather_rows: bad arguments");
@@ -446,6 +485,10 @@ int sdqlb200_comm_merge(void* vctx, uint64_t workspace_offset, uint64_t count, i
     int rc;
     if (op == SDQLB200_MERGE_TABLE) {
         rc = sdqlb200_comm_merge_table(x->comm, (const sdqlb200_table*)(uintptr_t)workspace_offset, x->stream);
+        x->table_merges += rc == 0;
+    } else if (op == SDQLB200_MERGE_DIRECT) {
+        rc = sdqlb200_comm_merge_direct(x->comm, (const sdqlb200_table*)(uintptr_t)workspace_offset, x->stream);
+        if (rc == 1) return 1;  // declined: the module all-reduces the arrays (counted there)
         x->table_merges += rc == 0;
     } else {
         rc = sdqlb200_comm_allreduce(x->comm, (char*)x->workspace + workspace_offset, count, op, x->stream);

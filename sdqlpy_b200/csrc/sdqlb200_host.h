@@ -214,6 +214,13 @@ static inline unsigned long long count_big_bytes() {
     if (v < 0) { const char* e = getenv("SDQLB200_COUNT_BIG_BYTES"); v = e ? atoll(e) : (4ll << 30); if (v < 0) v = 0; }
     return (unsigned long long)v;
 }
+// direct tables of at most this many slots are merged across ranks with ONE fused all-reduce (presence + all fields);
+// SDQLB200_FUSED_MERGE_MAX lowers it so that small-scale tests reach the large-table merges (sparse exchange / dense)
+static inline long long fused_merge_max() {
+    static long long v = -1;
+    if (v < 0) { const char* e = getenv("SDQLB200_FUSED_MERGE_MAX"); v = e ? atoll(e) : sdqlrt::kFusedMergeMaxSlots; if (v < 0 || v > sdqlrt::kFusedMergeMaxSlots) v = sdqlrt::kFusedMergeMaxSlots; }
+    return v;
+}
 static inline bool debug() {
     static const bool d = getenv("SDQLB200_DEBUG") && getenv("SDQLB200_DEBUG")[0] == '1';
     return d;

@@ -655,6 +655,45 @@ __global__ void k_tbl_absorb(TblIO t, const i64* rec, i64 n, int mode, int rank,
     }
 }
 
+// sparse merge of a DIRECT-indexed partial dictionary (SDQLB200_MERGE_DIRECT): records are (slot, owner rank, fields)
+__global__ void k_dtbl_count(TblIO t, u64* count) {
+    u64 c = 0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < t.cap; i += (i64)gridDim.x * blockDim.x) c += t.rep[i] >= 0;
+#ifndef SDQLB200_EMU
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+#else
+    *count += c;
+#endif
+}
+__global__ void k_dtbl_pack(TblIO t, int rank, u64* cursor, i64* rec) {
+    const int W = 2 + t.nf;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < t.cap; i += (i64)gridDim.x * blockDim.x) {
+        if (t.rep[i] < 0) continue;
+        i64* r = rec + atomicAdd(cursor, 1ull) * W;
+        r[0] = i;
+        r[1] = (i64)rank;
+        for (int j = 0; j < t.nf; ++j) r[2 + j] = (i64)t.agg[j][i];
+    }
+}
+// the OTHER ranks' records (lo <= index < hi skipped: this rank's own run): fields added in place, ownership settled --
+// an entry a lower rank also holds, or that this rank does not hold, becomes rep = -2 (present, iterated by its owner)
+__global__ void k_dtbl_absorb(TblIO t, const i64* rec, i64 n, i64 lo, i64 hi, int rank) {
+    const int W = 2 + t.nf;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        if (i >= lo && i < hi) continue;
+        const i64* r = rec + i * W;
+        const i64 slot = r[0];
+        for (int j = 0; j < t.nf; ++j) {
+            if ((t.f64_mask >> j) & 1u) red_add((double*)t.agg[j] + slot, __longlong_as_double(r[2 + j]));
+            else red_add((i64*)t.agg[j] + slot, r[2 + j]);
+        }
+        if ((int)r[1] < rank) t.rep[slot] = -2;       // (racing writers all store -2)
+        else atomicCAS(t.rep + slot, -1, -2);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // fixed-width, zero-padded byte strings (device form of VarChar<N>, 1 byte per char)
 // ---------------------------------------------------------------------------------------------

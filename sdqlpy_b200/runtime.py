@@ -849,6 +849,8 @@ class CompiledModule:
             d = D.dist
             ws = self.ws[1]
             t = ws if isinstance(ws, torch.Tensor) else torch.from_numpy(ws)
+            if op == 4:
+                return 1  # SDQLB200_MERGE_DIRECT: declined here (no communicator): the module all-reduces the arrays
             if op == 3:
                 self._merge_table(Table.from_address(off))
             elif op == 0:

@@ -129,3 +129,14 @@ def test_process_per_gpu_hash_all_to_all(tmp_path):
 def test_engine_four_gpus(tmp_path):
     res = _run(tmp_path, "engine", 4, 0.05)
     assert res["bad"] == [], res["bad"]
+
+
+def test_large_direct_tables_sparse_and_dense_merges(tmp_path):
+    """fused one-shot merge limited to 64 slots: every larger direct table goes through SDQLB200_MERGE_DIRECT -- the sparse
+    exchange of occupied slots where few are, the dense MIN / SUM all-reduces of the arrays elsewhere (both bootstraps)"""
+    env = {"SDQLB200_FUSED_MERGE_MAX": "64"}
+    res = _run(tmp_path, "engine", 2, 0.05, env, "_direct")
+    assert res["bad"] == [], res["bad"]
+    assert min(res["table_merges"]) > 1   # sparse direct merges are counted as table merges
+    res = _run(tmp_path, "procs", 2, 0.05, env, "_direct")
+    assert res["bad"] == [], res["bad"]

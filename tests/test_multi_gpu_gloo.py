@@ -105,3 +105,13 @@ def test_world2_merged_tables_are_counted_and_replanned_alike(emu_so, tmp_path, 
     bad, merges, tmerges = open(out).read().split("\n")
     assert bad == "[]", bad
     assert int(merges) > 0
+
+
+def test_world2_large_direct_tables_dense_merge(emu_so, tmp_path, monkeypatch):
+    """fused one-shot merge limited to 64 slots: larger direct tables take the owner-election + per-field all-reduce path
+    (the sparse exchange, SDQLB200_MERGE_DIRECT, needs the communicator and is declined here)"""
+    monkeypatch.setenv("SDQLB200_FUSED_MERGE_MAX", "64")
+    out = str(tmp_path / "res.txt")
+    mp.spawn(_worker, args=(2, emu_so, 29739, SUPPORTED, out), nprocs=2, join=True)
+    bad, merges, tmerges = open(out).read().split("\n")
+    assert bad == "[]", bad

@@ -67,7 +67,8 @@ def test_string_scan_bytes_are_counted(stats_module):
     cols, strs = roofline.scan_bytes(man, nrows)
     assert strs == 79 * nrows["ord"]          # o_comment is searched for every order
     assert cols == 4 * nrows["ord"] + 4 * nrows["cu"]
-    assert st["upserts"] > 0
+    assert st["finds"] > 0                    # customers probe the per-customer order counts (the group-bys run in the
+                                              # shared-memory tiers at this size: no global insert-or-find left to count)
 
 
 def test_regular_build_reports_init_bytes_only():
