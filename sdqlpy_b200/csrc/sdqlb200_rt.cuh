@@ -245,26 +245,35 @@ SDQL_DEV u64 hash64(u64 x) {  // splitmix64 finaliser
 // lies in -- four 8-byte keys, two 128-bit loads -- per memory round trip: the sector is what a random 8-byte read moves
 // anyway, and a probe chain of up to four slots inside it resolves without a second dependent load (what a 4-lane
 // cooperative group per key would achieve, without giving up 3 of 4 lanes to it).  Tables have >= 1024 slots (power of
-// two), so a group of four never wraps.  B200, SF100 (profiles/r02_visit10/r02_v10_ab_probe_sf100.json): q9_k5 6.85 ->
+// two), so a group never wraps.  kProbeKeys = 4 is the whole sector; -DSDQLB200_PROBE_KEYS=2 examines an aligned pair (one
+// 128-bit load, 4 registers less: inlined into every probe site the full group cost q19_k1 -- whose tables are direct or
+// tiny -- an occupancy step, 48 -> 60 registers, 2.12 -> 2.52 ms at SF100; an out-of-line probe cost every caller the ABI).  B200, SF100 (profiles/r02_visit10/r02_v10_ab_probe_sf100.json): q9_k5 6.85 ->
 // 6.46 ms, q20_k3 3.47 -> 3.17 ms, Q2 0.746 -> 0.717 ms against one slot per step (-DSDQLB200_PROBE_SLOT keeps that).
+#ifndef SDQLB200_PROBE_KEYS
+#define SDQLB200_PROBE_KEYS 2
+#endif
+constexpr int kProbeKeys = SDQLB200_PROBE_KEYS;
 SDQL_DEV int tbl_probe(const Tbl& t, u64 key) {
     const u64 m = (u64)t.cap - 1;
     u64 h = hash64(key) & m;
 #if !defined(SDQLB200_PROBE_SLOT) && !defined(SDQLB200_EMU)
     for (;;) {
         stat(kStFindSlots);
-        const u64 base = h & ~3ull;
-        const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(t.keys + base));
-        const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2*>(t.keys + base + 2));
-        const u64 k4[4] = {a.x, a.y, b.x, b.y};
+        const u64 base = h & ~(u64)(kProbeKeys - 1);
+        u64 k4[kProbeKeys];
+#pragma unroll
+        for (int j = 0; j < kProbeKeys; j += 2) {
+            const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(t.keys + base + j));
+            k4[j] = a.x; k4[j + 1] = a.y;
+        }
         const int j0 = (int)(h - base);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kProbeKeys; ++j) {
             if (j < j0) continue;
             if (k4[j] == key) return (int)(base + j);
             if (k4[j] == kEmpty) return -1;
         }
-        h = (base + 4) & m;
+        h = (base + kProbeKeys) & m;
     }
 #else
     for (;;) {
