@@ -37,6 +37,20 @@ int sdqlb200_ingest_ucs4_codes(const uint32_t* d_in, int64_t rows, int32_t nchar
                                int32_t out_width, unsigned long long* d_bad, void* stream);
 /* d_out[i] = d_table[d_in[i]] as uint8 (out_width 1) or int32 (4): provisional (first-seen) codes -> final dictionary order */
 int sdqlb200_ingest_remap(const int32_t* d_in, const int32_t* d_table, void* d_out, int32_t out_width, int64_t n, void* stream);
+/* d_out[i] = d_table256[d_in[i]]: bytes of a narrowed `<U1` column -> dictionary codes (in place allowed) */
+int sdqlb200_ingest_remap_u8(const uint8_t* d_in, const uint8_t* d_table256, uint8_t* d_out, int64_t n, void* stream);
+
+/* HOST side of the upload (round 2).  With the inputs in host memory on every call the step is bound by the PCIe link, and
+ * int64 keys / dates and UCS4 `<U1` flags carry 4 resp. 3 dead bytes per value across it.  These passes narrow such columns
+ * with `threads` host threads into (page-locked) staging buffers WHILE the fp64 columns -- which need no host work --
+ * occupy the link; the narrowed image then crosses instead of the raw one (Q1: 38 instead of 48 bytes per row).
+ * h_* are HOST pointers.  Both return 0, or SDQLB200_E_ARG. */
+/* int64 -> int32; minmax[0] = min, minmax[1] = max of the column (the caller range-checks: values are truncated) */
+int sdqlb200_ingest_host_i64(const int64_t* h_in, int32_t* h_out, int64_t n, int32_t threads, int64_t* minmax);
+/* `<U1` (one UCS4 code point per row) -> one byte per row; present[b >> 6] bit (b & 63) set for every byte value seen;
+ * *bad_row = first row with a code point > 255, or -1 */
+int sdqlb200_ingest_host_ucs4_1(const uint32_t* h_in, uint8_t* h_out, int64_t n, int32_t threads, uint64_t present[4],
+                                int64_t* bad_row);
 const char* sdqlb200_ingest_last_error(void);
 
 #ifdef __cplusplus

@@ -7,6 +7,8 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <thread>
+#include <vector>
 
 #include "sdqlb200.h"
 #include "sdqlb200_ingest.h"
@@ -144,9 +146,102 @@ __global__ void __launch_bounds__(kBlock) k_remap(const int* __restrict__ in, co
     }
 }
 
+__global__ void __launch_bounds__(kBlock) k_remap_u8(const unsigned char* __restrict__ in, const unsigned char* __restrict__ table,
+                                                     unsigned char* out, i64 n) {
+    __shared__ unsigned char lut[256];
+    lut[threadIdx.x] = table[threadIdx.x];  // kBlock == 256
+    __syncthreads();
+    const i64 nq = n >> 2, stride = (i64)gridDim.x * blockDim.x;
+    for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+        const unsigned w = __ldg((const unsigned*)in + q);
+        ((unsigned*)out)[q] = (unsigned)lut[w & 0xff] | ((unsigned)lut[(w >> 8) & 0xff] << 8) | ((unsigned)lut[(w >> 16) & 0xff] << 16) |
+                              ((unsigned)lut[w >> 24] << 24);
+    }
+    if (blockIdx.x == 0)
+        for (i64 i = (nq << 2) + threadIdx.x; i < n; i += blockDim.x) out[i] = lut[in[i]];
+}
+
+// [lo, hi) of worker w of nw over n items, in units of 64 (cache line of the narrow output)
+inline void host_slice(i64 n, int w, int nw, i64* lo, i64* hi) {
+    const i64 per = ((n + nw - 1) / nw + 63) & ~63ll;
+    *lo = per * w < n ? per * w : n;
+    *hi = per * (w + 1) < n ? per * (w + 1) : n;
+}
+
 }  // namespace
 
 extern "C" {
+
+int sdqlb200_ingest_remap_u8(const uint8_t* d_in, const uint8_t* d_table256, uint8_t* d_out, int64_t n, void* stream) {
+    if (n < 0 || (n > 0 && (!d_in || !d_out || !d_table256))) return fail(SDQLB200_E_ARG, "ingest_remap_u8: bad arguments");
+    if (((uintptr_t)d_in | (uintptr_t)d_out) & 3) return fail(SDQLB200_E_ARG, "ingest_remap_u8: pointers must be 4-byte aligned");
+    if (n == 0) return 0;
+    k_remap_u8<<<grid_for((n + 3) / 4), kBlock, 0, (cudaStream_t)stream>>>(d_in, d_table256, d_out, n);
+    ING_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int sdqlb200_ingest_host_i64(const int64_t* h_in, int32_t* h_out, int64_t n, int32_t threads, int64_t* minmax) {
+    if (n < 0 || (n > 0 && (!h_in || !h_out)) || !minmax) return fail(SDQLB200_E_ARG, "ingest_host_i64: bad arguments");
+    const int nw = threads < 1 ? 1 : threads > 256 ? 256 : threads;
+    std::vector<i64> mn(nw, 0x7fffffffffffffffll), mx(nw, -0x7fffffffffffffffll - 1);
+    auto work = [&](int w) {
+        i64 lo, hi;
+        host_slice(n, w, nw, &lo, &hi);
+        i64 a = 0x7fffffffffffffffll, b = -0x7fffffffffffffffll - 1;
+        for (i64 i = lo; i < hi; ++i) {  // vectorises: 64-bit min / max + truncating store
+            const i64 v = h_in[i];
+            a = v < a ? v : a;
+            b = v > b ? v : b;
+            h_out[i] = (int32_t)v;
+        }
+        mn[w] = a; mx[w] = b;
+    };
+    std::vector<std::thread> th;
+    for (int w = 1; w < nw; ++w) th.emplace_back(work, w);
+    work(0);
+    for (auto& t : th) t.join();
+    i64 a = mn[0], b = mx[0];
+    for (int w = 1; w < nw; ++w) { a = mn[w] < a ? mn[w] : a; b = mx[w] > b ? mx[w] : b; }
+    minmax[0] = a; minmax[1] = b;
+    return 0;
+}
+
+int sdqlb200_ingest_host_ucs4_1(const uint32_t* h_in, uint8_t* h_out, int64_t n, int32_t threads, uint64_t present[4],
+                                int64_t* bad_row) {
+    if (n < 0 || (n > 0 && (!h_in || !h_out)) || !present || !bad_row) return fail(SDQLB200_E_ARG, "ingest_host_ucs4_1: bad arguments");
+    const int nw = threads < 1 ? 1 : threads > 256 ? 256 : threads;
+    std::vector<uint64_t> pr((size_t)nw * 4, 0);
+    std::vector<i64> bad(nw, -1);
+    auto work = [&](int w) {
+        i64 lo, hi;
+        host_slice(n, w, nw, &lo, &hi);
+        bool seen[256] = {false};
+        unsigned big = 0;
+        for (i64 i = lo; i < hi; ++i) {
+            const unsigned v = h_in[i];
+            big |= v;
+            h_out[i] = (uint8_t)v;
+            seen[v & 0xff] = true;
+        }
+        if (big > 255u)
+            for (i64 i = lo; i < hi; ++i)
+                if (h_in[i] > 255u) { bad[w] = i; break; }
+        for (int b = 0; b < 256; ++b)
+            if (seen[b]) pr[(size_t)w * 4 + (b >> 6)] |= 1ull << (b & 63);
+    };
+    std::vector<std::thread> th;
+    for (int w = 1; w < nw; ++w) th.emplace_back(work, w);
+    work(0);
+    for (auto& t : th) t.join();
+    present[0] = present[1] = present[2] = present[3] = 0;
+    *bad_row = -1;
+    for (int w = 0; w < nw; ++w) {
+        for (int k = 0; k < 4; ++k) present[k] |= pr[(size_t)w * 4 + k];
+        if (bad[w] >= 0 && (*bad_row < 0 || bad[w] < *bad_row)) *bad_row = bad[w];
+    }
+    return 0;
+}
 
 const char* sdqlb200_ingest_last_error(void) { return g_err; }
 

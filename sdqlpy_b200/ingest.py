@@ -31,6 +31,9 @@ def lib():
         L.sdqlb200_ingest_ucs4_distinct.argtypes = [vp, i64, i64, i32, vp, vp, i64, vp, vp]
         L.sdqlb200_ingest_ucs4_codes.argtypes = [vp, i64, i32, vp, vp, i64, vp, vp, i32, vp, vp]
         L.sdqlb200_ingest_remap.argtypes = [vp, vp, vp, i32, i64, vp]
+        L.sdqlb200_ingest_remap_u8.argtypes = [vp, vp, vp, i64, vp]
+        L.sdqlb200_ingest_host_i64.argtypes = [vp, vp, i64, i32, vp]
+        L.sdqlb200_ingest_host_ucs4_1.argtypes = [vp, vp, i64, i32, vp, vp]
         L.sdqlb200_ingest_last_error.restype = ctypes.c_char_p
         _lib = L
     return _lib
@@ -158,3 +161,86 @@ def recode(col_holder, n, width, table, be):
     tb = t.from_numpy(np.ascontiguousarray(table, dtype=np.int32)).to(be.dev)
     _ck(lib().sdqlb200_ingest_remap(src.data_ptr(), tb.data_ptr(), out.data_ptr(), w, n, be.stream()), "ingest_remap")
     return out.data_ptr(), out, w
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side narrowing in front of the upload (include/sdqlb200_ingest.h, "HOST side of the upload")
+# ---------------------------------------------------------------------------------------------
+_staging = {}  # (device, dtype, rows) -> page-locked staging tensors (reused: pinning gigabytes is slow)
+
+
+def host_threads():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    return max(1, min(n, int(os.environ.get("SDQLB200_HOST_THREADS", "16"))))
+
+
+class HostNarrow:
+    """int64 -> int32 / `<U1` -> byte narrowing of one host column by host threads, started in the background (the C call
+    releases the GIL) so that columns which need no host work cross the link meanwhile; finish() uploads the narrowed image.
+    -> (device pointer, holder, min, max, element bytes, dictionary, bytes over the link), or None when the column turned out
+    not to be narrowable (a `<U1` code point > 255: the device-side encoder takes it)."""
+
+    def __init__(self, a, rep, be):
+        import threading
+        t = be.torch
+        self.a, self.rep, self.be, self.n = np.ascontiguousarray(a), rep, be, len(a)
+        dt = t.int32 if rep == "i32" else t.uint8
+        key = (str(be.dev), str(dt), self.n)
+        pool = _staging.setdefault(key, [])
+        self.stage = pool.pop() if pool else t.empty(max(self.n, 4), dtype=dt, pin_memory=True)
+        self.key = key
+        self.mm = np.zeros(2, dtype=np.int64)
+        self.present = np.zeros(4, dtype=np.uint64)
+        self.bad = np.full(1, -1, dtype=np.int64)
+        self.rc = None
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def _run(self):
+        L = lib()
+        if self.rep == "i32":
+            self.rc = L.sdqlb200_ingest_host_i64(self.a.ctypes.data, self.stage.data_ptr(), self.n, host_threads(), self.mm.ctypes.data)
+        else:
+            self.rc = L.sdqlb200_ingest_host_ucs4_1(self.a.ctypes.data, self.stage.data_ptr(), self.n, host_threads(),
+                                                    self.present.ctypes.data, self.bad.ctypes.data)
+
+    def finish(self):
+        self.th.join()
+        t, be, n = self.be.torch, self.be, self.n
+        try:
+            _ck(self.rc, "ingest_host")
+            if self.rep == "i32":
+                mn, mx = (int(self.mm[0]), int(self.mm[1])) if n else (0, 0)
+                if n and (mn < -2**31 or mx >= 2**31):
+                    raise ValueError("integer column outside int32 range (device layout is int32 in this version)")
+                out = t.empty(max(n, 4), dtype=t.int32, device=be.dev)
+                out[:n].copy_(self.stage[:n], non_blocking=True)
+                self._release(out)
+                return out.data_ptr(), out, mn, mx, 4, None, 4 * n
+            if int(self.bad[0]) >= 0:
+                self._release(None)
+                return None
+            values = [b for b in range(256) if (int(self.present[b >> 6]) >> (b & 63)) & 1]
+            dictionary = ["" if b == 0 else chr(b) for b in values]  # np.unique order: code points ascending
+            table = np.zeros(256, dtype=np.uint8)
+            for code, b in enumerate(values):
+                table[b] = code
+            out = t.empty(max(n, 4), dtype=t.uint8, device=be.dev)
+            out[:n].copy_(self.stage[:n], non_blocking=True)
+            tb = t.from_numpy(table).to(be.dev)
+            _ck(lib().sdqlb200_ingest_remap_u8(out.data_ptr(), tb.data_ptr(), out.data_ptr(), n, be.stream()), "ingest_remap_u8")
+            self._release(out)
+            return out.data_ptr(), out, 0, max(0, len(dictionary) - 1), 1, dictionary, n
+        except Exception:
+            self._release(None)
+            raise
+
+    def _release(self, dev_tensor):
+        """the staging buffer goes back to the pool once the copy out of it has run"""
+        if dev_tensor is not None:
+            self.be.torch.cuda.current_stream().synchronize()
+        _staging.setdefault(self.key, []).append(self.stage)
+        self.stage = None

@@ -175,6 +175,9 @@ class DeviceColumn:
 
 
 STRIDE = os.environ.get("SDQLB200_STRIDE", "1") != "0"
+# host-side narrowing of int64 / `<U1` columns in front of the upload (ingest.HostNarrow): see ColumnStore.get_many
+HOST_NARROW = os.environ.get("SDQLB200_HOST_NARROW", "0") == "1"
+HOST_NARROW_MIN_ROWS = int(os.environ.get("SDQLB200_HOST_NARROW_MIN_ROWS", str(1 << 20)))
 
 
 def stride_stat(values, mn):
@@ -342,6 +345,44 @@ class ColumnStore:
         if self.enabled:
             self.cache[k] = (col, src)  # keep the host object alive so the identity key stays valid
         return col
+
+    def get_many(self, items):
+        """the columns of one query: [(src, rep, width, shared)] -> [DeviceColumn].  With SDQLB200_HOST_NARROW=1, big int64 / `<U1`
+        numpy columns that are not resident yet are narrowed by host threads (ingest.HostNarrow, background) while the columns
+        that need no host work -- fp64 -- already cross the link; their narrowed images follow."""
+        out = [None] * len(items)
+        pending = []
+        if HOST_NARROW:
+            be = backend()
+            if be.name == "cuda":
+                from . import ingest
+                for i, (src, rep, width, shared) in enumerate(items):
+                    if not isinstance(src, np.ndarray) or len(src) < HOST_NARROW_MIN_ROWS:
+                        continue
+                    if self.enabled and (self.key(src), rep, width) in self.cache:
+                        continue
+                    if (rep == "i32" and src.dtype == np.int64) or (rep == "code" and src.dtype == np.dtype("<U1")):
+                        pending.append((i, ingest.HostNarrow(src, rep, be)))
+        started = {i for i, _ in pending}
+        for i, (src, rep, width, shared) in enumerate(items):
+            if i not in started:
+                out[i] = self.get(src, rep, width, shared)
+        for i, job in pending:
+            src, rep, width, shared = items[i]
+            res = job.finish()
+            if res is None:  # not narrowable after all (a code point > 255): the device path
+                out[i] = self.get(src, rep, width, shared)
+                continue
+            ptr, holder, mn, mx, w, d, h2d = res
+            self.h2d_bytes += h2d
+            col = DeviceColumn(rep, ptr, holder, len(src), mn, mx, w, d, len(src) * w,
+                               stride_stat(holder[:len(src)], mn) if rep == "i32" else 0)
+            if shared is not None and rep == "code":
+                self._share_dictionary(col, shared, be)
+            if self.enabled:
+                self.cache[(self.key(src), rep, width)] = (col, src)
+            out[i] = col
+        return out
 
     @staticmethod
     def _share_dictionary(col, D, be):
@@ -740,14 +781,15 @@ class CompiledModule:
         argpos = {a: i for i, a in enumerate(q["args"])}
         if len(db) != len(q["args"]):
             raise ValueError("%s expects %d relations, got %d" % (name, len(q["args"]), len(db)))
-        cols = []
+        items = []
         for arg, col, rep in q["inputs"]:
             names = [c for c, _ in q["schemas"][arg]]
             kind = dict((c, k) for c, k in q["schemas"][arg])[col]
             width = kind[1] if isinstance(kind, list) else 0
             Dsh = dist_config()
             shared = Dsh if (Dsh is not None and Dsh.world > 1 and arg in Dsh.partitioned) else None
-            cols.append(STORE.get(db[argpos[arg]][names.index(col)], rep, width, shared))
+            items.append((db[argpos[arg]][names.index(col)], rep, width, shared))
+        cols = STORE.get_many(items)
         nrows = []
         for a in q["args"]:
             # row count: first available column (the reference reads it from column 0, sdql_compiler.py:644)

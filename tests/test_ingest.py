@@ -74,3 +74,69 @@ def test_ingest_errors(cuda_be, monkeypatch):
     col = runtime.STORE.get(many, "code", 0)
     assert col.dictionary == sorted(many.tolist()) and col.width == 1
     runtime.STORE.clear()
+
+
+def test_host_narrowing_passes():
+    """the host side of the upload (sdqlb200_ingest_host_*: plain C++ threads in the ingest library, no device involved):
+    int64 -> int32 with min / max, <U1 -> bytes with the set of bytes present and the first row that does not fit a byte"""
+    lib = ctypes.CDLL(build.compile_ingest())
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    lib.sdqlb200_ingest_host_i64.argtypes = [vp, vp, i64, i32, vp]
+    lib.sdqlb200_ingest_host_ucs4_1.argtypes = [vp, vp, i64, i32, vp, vp]
+    rng = np.random.default_rng(7)
+    for n in (0, 1, 63, 64, 65, 1000, 100003):
+        a = rng.integers(-2**31, 2**31, n, dtype=np.int64)
+        out, mm = np.full(max(n, 1), 123, dtype=np.int32), np.zeros(2, dtype=np.int64)
+        for th in (1, 3, 8):
+            assert lib.sdqlb200_ingest_host_i64(a.ctypes.data, out.ctypes.data, n, th, mm.ctypes.data) == 0
+            assert np.array_equal(out[:n], a.astype(np.int32))
+            if n:
+                assert (int(mm[0]), int(mm[1])) == (int(a.min()), int(a.max()))
+        u = rng.choice(np.array(["A", "N", "R", ""], dtype="<U1"), n)
+        o8, pr, bad = np.full(max(n, 1), 9, dtype=np.uint8), np.zeros(4, dtype=np.uint64), np.zeros(1, dtype=np.int64)
+        for th in (1, 5):
+            assert lib.sdqlb200_ingest_host_ucs4_1(u.ctypes.data, o8.ctypes.data, n, th, pr.ctypes.data, bad.ctypes.data) == 0
+            assert np.array_equal(o8[:n], u.view(np.uint32).astype(np.uint8)) and int(bad[0]) == -1
+            present = {b for b in range(256) if (int(pr[b >> 6]) >> (b & 63)) & 1}
+            assert present == {int(x) for x in np.unique(u.view(np.uint32))}
+        if n > 10:
+            u[n // 2], u[n - 1] = "Ж", "€"
+            lib.sdqlb200_ingest_host_ucs4_1(u.ctypes.data, o8.ctypes.data, n, 4, pr.ctypes.data, bad.ctypes.data)
+            assert int(bad[0]) == n // 2
+
+
+@pytest.mark.gpu
+def test_host_narrowed_upload_equals_device_ingest(cuda_be, monkeypatch):
+    """SDQLB200_HOST_NARROW path of ColumnStore.get_many: the same resident columns, statistics and dictionaries as the
+    device-side ingest, with fewer bytes over the link; a query through it matches the golden"""
+    from compare import compare
+    from util import QUERY_SCRIPT, golden
+    import ref_runner as rr
+    monkeypatch.setattr(runtime, "HOST_NARROW", True)
+    monkeypatch.setattr(runtime, "HOST_NARROW_MIN_ROWS", 1)
+    li = ref_db(0.05, ["lineitem"])[0]
+    runtime.STORE.clear()
+    items = [(li[10], "i32", 0, None), (li[4], "f64", 0, None), (li[8], "code", 1, None), (li[9], "code", 1, None), (li[0], "i32", 0, None)]
+    h0 = runtime.STORE.h2d_bytes
+    got = runtime.STORE.get_many(items)
+    narrowed = runtime.STORE.h2d_bytes - h0
+    runtime.STORE.clear()
+    monkeypatch.setattr(runtime, "HOST_NARROW", False)
+    h0 = runtime.STORE.h2d_bytes
+    want = runtime.STORE.get_many(items)
+    raw = runtime.STORE.h2d_bytes - h0
+    n = len(li[0])
+    assert narrowed == n * (4 + 8 + 1 + 1 + 4) and raw == n * (8 + 8 + 4 + 4 + 8)
+    for g, w in zip(got, want):
+        assert (g.kind, g.rows, g.min, g.max, g.width, g.dictionary, g.stride) == (w.kind, w.rows, w.min, w.max, w.width, w.dictionary, w.stride)
+        assert np.array_equal(g.holder[:n].cpu().numpy(), w.holder[:n].cpu().numpy())
+    runtime.STORE.clear()
+    monkeypatch.setattr(runtime, "HOST_NARROW", True)
+    mod = runtime.load_compiled(QUERY_SCRIPT)
+    for q in ("q1", "q12"):
+        assert compare(mod.run(q, ref_db(0.05, rr.QUERY_ARGS[q])), golden(0.05)[q]) is None
+    # a <U1 column with a code point that does not fit a byte takes the device-side encoder
+    odd = np.array(["A", "Ж", "A", "B"] * 10, dtype="<U1")
+    col = runtime.STORE.get_many([(odd, "code", 1, None)])[0]
+    assert col.dictionary == ["A", "B", "Ж"]
+    runtime.STORE.clear()
