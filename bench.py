@@ -494,11 +494,12 @@ def main():
         ok = "ok" if (isinstance(r, float) or r.size() == res_q.size()) else "row count differs from the resident run"
         e2e = {"value": all_bytes / e2e_s / 1e9, "unit": "GB/s", "ms_per_step": e2e_s * 1e3,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(mod.last.d2h_bytes),
-               "host_layout": "numpy int64 / float64 / <U1 (reference layout, %d B/row over PCIe), page-locked" % (h2d // max(1, rows)),
+               "host_layout": "numpy int64 / float64 / <U1 (reference layout, 48 B/row in host memory, page-locked); %d B/row cross PCIe" % (h2d // max(1, rows)),
                "result": ok, "host_columns_s": round(t_host, 1),
-               "note": "every step: <fn>_compiled(db) with plain numpy columns -> raw bytes over PCIe in 512 MB chunks -> int64->int32 / "
-                       "<U1->code conversion on the device (csrc/sdqlb200_ingest.cu) -> query -> result rows to the host; %d steps; value = "
-                       "resident-layout bytes / time (same numerator as 'value' and as the reference arm)" % args.e2e_steps}
+               "note": "every step: <fn>_compiled(db) with plain numpy columns -> fp64 columns over PCIe as they are while host threads "
+                       "narrow the int64 / <U1 columns (int32 / bytes, csrc/sdqlb200_ingest.cu host side), their images follow -> dictionary "
+                       "codes on the device -> query -> result rows to the host; %d steps; value = resident-layout bytes / time (same "
+                       "numerator as 'value' and as the reference arm)" % args.e2e_steps}
         runtime.STORE.enabled = True
         runtime.STORE.clear()
         # ---- the reference's CPU path on the same host columns (rank 0, N = 1) ------------------------------------------

@@ -618,6 +618,8 @@ class Kernel:
                 L += prefetches()
                 L += loads("r_", "g", "        ")
             L += ["        " + x for x in self.iter_pre]
+            if self.body2 is not None:
+                L.append("        unsigned pm_ = 0u;  // bit u: row u of this lane survived the filter")
             L.append("#pragma unroll")
             L.append("        for (int u = 0; u < %d; ++u) {" % R)
             L.append("            const %s i = ((g + (u >> 2) * (%s)blockDim.x) << 2) + (u & 3);" % (IT, IT))
@@ -626,13 +628,22 @@ class Kernel:
             L.append("            if (i < n) {")
             L += ["                " + x for x in self.body]
             L.append("            }")
-            if self.body2 is not None:  # warp-aggregated push of the surviving row ids
-                L.append("            {")
-                L.append("                const unsigned m_ = sdqlrt::warp_ballot(pass_);")
-                L.append("                if (pass_) wq[wcnt + __popc(m_ & ((1u << lane_) - 1u))] = (int)i;")
+            if self.body2 is not None:
+                L.append("            pm_ |= (pass_ ? 1u : 0u) << u;")
+            L.append("        }")
+            if self.body2 is not None:
+                # warp-aggregated push of the surviving row ids.  One vote decides whether any of the warp's 32 x R rows
+                # survived: behind a selective filter (Q17: 0.1 %) nearly every step skips the R ballots / popcounts / stores
+                L.append("        if (sdqlrt::warp_ballot(pm_ != 0u)) {")
+                L.append("#pragma unroll")
+                L.append("            for (int u = 0; u < %d; ++u) {" % R)
+                L.append("                const %s i = ((g + (u >> 2) * (%s)blockDim.x) << 2) + (u & 3);" % (IT, IT))
+                L.append("                const bool p_ = (pm_ >> u) & 1u;")
+                L.append("                const unsigned m_ = sdqlrt::warp_ballot(p_);")
+                L.append("                if (p_) wq[wcnt + __popc(m_ & ((1u << lane_) - 1u))] = (int)i;")
                 L.append("                wcnt += __popc(m_);")
                 L.append("            }")
-            L.append("        }")
+                L.append("        }")
             L += ["        " + x for x in self.iter_post]
             if RECONVERGE:
                 L.append("        sdqlrt::warp_sync();  // lanes that took a slow path rejoin the warp here")
