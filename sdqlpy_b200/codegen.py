@@ -75,8 +75,6 @@ TEXTALIGNED = os.environ.get("SDQLB200_TEXTALIGNED", "1") != "0"
 # warp: ncu showed q12_k0's main loop executing with 13 of 32 lanes active and 2.5x the warp-level instructions of the
 # cardinality pass over the same rows (profiles/r01_q12_k0_main_*.txt; SF100: 15.0 ms vs 1.3 ms).
 RECONVERGE = os.environ.get("SDQLB200_RECONVERGE", "1") != "0"
-# selective single-key tables get a Bloom summary in the probing kernel's shared memory (sdqlrt::k_tbl_bloom / tbl_find1)
-SMEM_BLOOM = os.environ.get("SDQLB200_SMEM_BLOOM", "1") != "0"
 # probes of single-part tables with an int32 column value use 32-bit key arithmetic (sdqlrt::pack_key1 / tbl_find1): the
 # narrow lineitem scans are bound by instruction issue (~3 warp instructions per row, profiles/r01_q5_k5_narrow_*.txt),
 # most of them 64-bit key packing and the generic presence test
@@ -485,14 +483,9 @@ class Kernel:
         tmpl = "template <int TIER>\n" if self.templated else ""
         L.append("%s__global__ void __launch_bounds__(sdqlrt::kBlock) %s(const __grid_constant__ %s_ctx c) {" %
                  (tmpl, self.name, q.name))
-        bloom_tabs = getattr(self, "bloom_tabs", None) or []
-        if self.tiered or self.pipe_mode() == "tma" or self.byte_cols or self.text_cols or self.body2 is not None or bloom_tabs:
+        if self.tiered or self.pipe_mode() == "tma" or self.byte_cols or self.text_cols or self.body2 is not None:
             L.append("    SDQL_EXTERN_SMEM(sm);")
         L += ["    " + s for s in self.pre]
-        for t in bloom_tabs:  # the table's Bloom summary, staged in this CTA's shared memory (nullptr: the table has none)
-            L.append("    unsigned* const sbl_%s = c.%s_bl ? (unsigned*)((unsigned char*)sm + c.%s_blo) : nullptr;" % (t.name, t.name, self.name))
-            L.append("    if (sbl_%s) { for (int k = threadIdx.x; k < (1 << (c.%s_bll - 5)); k += blockDim.x) sbl_%s[k] = c.%s_bl[k]; __syncthreads(); }" %
-                     (t.name, t.name, t.name, t.name))
         if self.src[0] == "rel" and self.pipe_mode() == "tma":
             L += self.render_ring()
         elif self.src[0] == "rel":
@@ -1700,18 +1693,7 @@ class Query:
             else:
                 sl = K.tmp("sl")
                 if fast1:
-                    bl = getattr(K, "bloom_tabs", None)
-                    if (SMEM_BLOOM and K.src[0] == "rel" and K.pipe_mode() != "tma" and t.builder is not None and t.builder.counted
-                            and (bl is None or t in bl or len(bl) < 1)):
-                        if bl is None:
-                            bl = K.bloom_tabs = []
-                        if t not in bl:
-                            bl.append(t)
-                            t.bloom_users = getattr(t, "bloom_users", []) + [K]
-                        K.emit("const int %s = sdqlrt::tbl_find1(c.%s, (unsigned)%s, %s_ok, sbl_%s, c.%s_bll);" %
-                               (sl, t.name, kk, kk, t.name, t.name))
-                    else:
-                        K.emit("const int %s = sdqlrt::tbl_find1(c.%s, (unsigned)%s, %s_ok);" % (sl, t.name, kk, kk))
+                    K.emit("const int %s = sdqlrt::tbl_find1(c.%s, (unsigned)%s, %s_ok);" % (sl, t.name, kk, kk))
                 else:
                     K.emit("const int %s = sdqlrt::tbl_find(c.%s, %s, %s_ok, %s_p0);" % (sl, t.name, kk, kk, kk))
             hit = (sl, tok)
@@ -2129,12 +2111,6 @@ def render_query(q):
         for j, (_, ct) in enumerate(t.fields):
             L.append("    %s* %s_a%d;" % (CT[ct], t.name, j))
         L.append("    int %s_all;  // multi-GPU: the table was merged across ranks and every rank iterates ALL of its entries" % t.name)
-    for t in q.tables:
-        if getattr(t, "bloom_users", None):
-            L.append("    const unsigned* %s_bl; int %s_bll;  // Bloom summary of %s (2^bll bits), nullptr = none" % (t.name, t.name, t.name))
-    for K in q.kernels:
-        if getattr(K, "bloom_tabs", None):
-            L.append("    unsigned %s_blo;  // offset of the staged Bloom summary in dynamic shared memory" % K.name)
     if any(late_domain(t) for t in q.tables):
         L.append("    long long* mm;  // {min, max} of the aggregate values a late key domain comes from")
     for K in q.kernels:
@@ -2227,9 +2203,6 @@ def render_query(q):
         L.append("    int* own_%s = a->merge ? ar.alloc<int>(c.%s.cap) : nullptr;" % (t.name, t.name))
         L.append("    double* mg_%s = (a->merge && c.%s.cap <= sdqlhost::fused_merge_max()) ? ar.alloc<double>(c.%s.cap * %d) : nullptr;" %
                  (t.name, t.name, t.name, 1 + nf64 + 2 * (len(t.fields) - nf64)))
-    for t in q.tables:
-        if getattr(t, "bloom_users", None):
-            L.append("    unsigned* bl_%s = ar.alloc<unsigned>(16384);  // up to 2^19 bits" % t.name)
     L.append("    const unsigned long long tail_off = ar.used;  // scalars, counters, partials: zeroed before every run")
     L.append("    c.sc = ar.alloc<double>(%d); c.cnt = ar.alloc<unsigned>(%d); c.tcount = ar.alloc<unsigned long long>(%d);" %
              (max(1, q.nsc), max(1, q.ncnt), max(1, q.ntcount)))
@@ -2310,8 +2283,6 @@ def render_query(q):
     L.append("    const unsigned pm = a->merge ? a->part_mask : 0u;  // multi-GPU: which relation arguments are partitioned")
     for t in q.tables:
         L.append("    bool part_%s = false;" % t.name)
-        if getattr(t, "bloom_users", None):
-            L.append("    long long ent_%s = -1;  // rows that reached its build (cardinality pass), -1 = not counted" % t.name)
     for K in q.kernels:
         if K.src[0] == "rel":
             L.append("    const bool part_%s = (pm >> %d) & 1u;" % (K.name, q.args.index(K.src[1])))
@@ -2402,16 +2373,6 @@ def render_query(q):
             L.append("        SDQL_CUDA(sdqlhost_init_table(a->workspace, tr[%d], st));" % t.index)
             L.append("        sdqlhost_step(st, \"%s:key-domain\");" % K.name)
             L.append("    }")
-        for t in getattr(K, "bloom_tabs", None) or []:
-            L.append("    if (c.%s_bl) {  // room for the table's Bloom summary behind the kernel's other shared memory" % t.name)
-            L.append("        c.%s_blo = (unsigned)((sm_%s + 15) & ~(size_t)15); sm_%s = c.%s_blo + ((size_t)1 << (c.%s_bll - 3));" %
-                     (K.name, K.name, K.name, K.name, t.name))
-            insts = (["%s<0>" % K.name, "%s<1>" % K.name, "%s<2>" % K.name] if K.tiered else ["%s<2>" % K.name]) if K.templated else [K.name]
-            if K.templated and K.count_ok:
-                insts.append("%s<3>" % K.name)
-            for fn_ in insts:
-                L.append("        sdqlhost_occupancy((const void*)%s, sm_%s);  // raises the dynamic shared memory limit" % (fn_, K.name))
-            L.append("    }")
         bits_tabs = [t for t in owned.get(K, []) if getattr(t, "want_bits", False)]
         if K.count_ok or bits_tabs:
             pe = part_expr(K)
@@ -2427,7 +2388,7 @@ def render_query(q):
             L.append("    if (late_%s) {" % K.name)
             L.append("        const bool merged_ = merged_%s;" % K.name)
             L.append("        if (merged_ ? cntm_%s : cnt_%s) {" % (K.name, K.name))
-            uses_smem = bool(K.byte_cols or K.text_cols or K.body2 is not None or getattr(K, "bloom_tabs", None))
+            uses_smem = bool(K.byte_cols or K.text_cols or K.body2 is not None)
             if uses_smem:  # same shared-memory layout as the real launch (queues / staging sit behind the tier table)
                 L.append("            sdqlhost_occupancy((const void*)%s<3>, sm_%s);  // raises the dynamic shared memory limit" % (K.name, K.name))
             L.append("            SDQL_LAUNCH(%s<3>, g_%s, sdqlrt::kBlock, %s, st, c);" % (K.name, K.name, "sm_%s" % K.name if uses_smem else "0"))
@@ -2446,8 +2407,6 @@ def render_query(q):
                 L.append("                if (sdqlhost::debug()) fprintf(stderr, \"[sdqlb200] %s: %%llu rows reach the build of %s -> %%s, %%lld slots%%s\\n\", h_cnt, c.%s.direct ? \"direct\" : \"hash\", (long long)c.%s.cap, rp_ ? \" (re-planned)\" : \"\");" % (K.name, t.name, t.name, t.name))
                 for j, (_, ct) in enumerate(t.fields):
                     L.append("                c.%s_a%d = (%s*)ag[%d];" % (t.name, j, CT[ct], j))
-                if getattr(t, "bloom_users", None):
-                    L.append("                if (!merged_) ent_%s = (long long)h_cnt;" % t.name)
                 if getattr(t, "want_bits", False):
                     # the new layout brought the presence filter back: still none for a merged table (the merge adds the
                     # other ranks' keys behind the bitmap's back -- probes for them would miss: Q20 on 2 GPUs lost 28 % of its rows)
@@ -2473,19 +2432,6 @@ def render_query(q):
         for t in bits_tabs:  # presence bits of the finished table (one pass over its slots; never for merged tables)
             L.append("    if (c.%s.bits) { SDQL_LAUNCH(sdqlrt::k_tbl_bits, sdqlhost::grid_for(c.%s.cap, 8, sms), sdqlrt::kBlock, 0, st, c.%s); SDQL_CUDA(cudaGetLastError()); }" %
                      (t.name, t.name, t.name))
-        for t in owned.get(K, []):
-            if getattr(t, "bloom_users", None):
-                L.append("    if (c.%s.bits && ent_%s >= 0 && ent_%s <= 131072) {  // small selective table: Bloom summary for shared memory" %
-                         (t.name, t.name, t.name))
-                L.append("        int lg_ = 15; while ((16ll * ent_%s) > (1ll << lg_) && lg_ < 19) ++lg_;" % t.name)
-                L.append("        SDQL_CUDA(cudaMemsetAsync(bl_%s, 0, (size_t)1 << (lg_ - 3), st));" % t.name)
-                L.append("        SDQL_LAUNCH(sdqlrt::k_tbl_bloom, sdqlhost::grid_for(c.%s.cap, 8, sms), sdqlrt::kBlock, 0, st, c.%s, bl_%s, lg_);" %
-                         (t.name, t.name, t.name))
-                L.append("        SDQL_CUDA(cudaGetLastError());")
-                L.append("        c.%s_bl = bl_%s; c.%s_bll = lg_;" % (t.name, t.name, t.name))
-                L.append("        if (sdqlhost::debug()) fprintf(stderr, \"[sdqlb200] %s: Bloom summary of %s, %%lld entries -> 2^%%d bits\\n\", ent_%s, lg_);" %
-                         (K.name, t.name, t.name))
-                L.append("    }")
         if bits_tabs:
             L.append("    sdqlhost_step(st, \"%s:bits\");" % K.name)
         # the kernel's own time ends here: the cross-GPU merge that follows is charged to the next interval

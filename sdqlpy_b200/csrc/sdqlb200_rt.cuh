@@ -313,29 +313,6 @@ SDQL_DEV bool pack_key1(int x, i64 mn, i64 rng, int sb, int sk, u64& key) {
     key = d;
     return ok && (u64)d < (u64)rng;
 }
-// Shared-memory summary of a small selective table (round 2): a one-hash Bloom filter of 2^lg bits (4 .. 64 KB) over the packed
-// keys, built once behind the table's build (k_tbl_bloom) and copied into every probing CTA's shared memory.  A narrow scan
-// that probes by a non-clustered key otherwise fetches one 32-byte L2 sector per row for a 4-byte bitmap word -- 600 M rows x
-// 32 B = 19 GB through L2, ~2.2 ms per lineitem pass at SF100 whatever the table holds; with <= 6 % false positives (16 bits
-// per entry) the sector is fetched for the rows that can match only.
-SDQL_DEV unsigned bloom_pos(unsigned key, int lg) { return (key * 0x9E3779B1u) >> (32 - lg); }
-SDQL_DEV int tbl_find1(const Tbl& t, unsigned d, bool ok);
-SDQL_DEV int tbl_find1(const Tbl& t, unsigned d, bool ok, const unsigned* sbloom, int lg) {
-    if (sbloom && ok) {
-        const unsigned p = bloom_pos(d, lg);
-        if (!((sbloom[p >> 5] >> (p & 31u)) & 1u)) return -1;
-    }
-    return tbl_find1(t, d, ok);
-}
-__global__ void k_tbl_bloom(Tbl t, unsigned* bloom, int lg) {
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < t.cap; i += (i64)gridDim.x * blockDim.x) {
-        u64 key;
-        if (t.direct) { if (t.rep[i] == -1) continue; key = (u64)i; }
-        else { key = t.keys[i]; if (key == kEmpty) continue; }
-        const unsigned p = bloom_pos((unsigned)key, lg);
-        atomicOr(bloom + (p >> 5), 1u << (p & 31u));
-    }
-}
 SDQL_DEV int tbl_find1(const Tbl& t, unsigned d, bool ok) {
     if (!ok) return -1;
     if (t.bits) {
