@@ -177,7 +177,11 @@ class DeviceColumn:
 STRIDE = os.environ.get("SDQLB200_STRIDE", "1") != "0"
 # host-side narrowing of int64 / `<U1` columns in front of the upload (ingest.HostNarrow): see ColumnStore.get_many
 # (B200 box, 16 host cores, Q1 at SF100 end to end: 547 -> 430 ms per step, 28.8 -> 22.8 GB over the link; profiles/r02_visit16)
-HOST_NARROW = os.environ.get("SDQLB200_HOST_NARROW", "1") != "0"
+# ... with 16 host threads for one rank.  Eight ranks on a 32-core box (4 threads each, the host's memory side already the
+# limit of the 8 concurrent uploads) lose with it: 100.8 -> 75.9 GB/s end to end (profiles/r02_visit14 / r02_visit18).
+# "auto" (default): narrow when the rank has at least HOST_NARROW_MIN_THREADS host threads to itself; "1" / "0": always / never
+HOST_NARROW = os.environ.get("SDQLB200_HOST_NARROW", "auto")
+HOST_NARROW_MIN_THREADS = int(os.environ.get("SDQLB200_HOST_NARROW_MIN_THREADS", "8"))
 HOST_NARROW_MIN_ROWS = int(os.environ.get("SDQLB200_HOST_NARROW_MIN_ROWS", str(1 << 20)))
 
 
@@ -353,10 +357,10 @@ class ColumnStore:
         that need no host work -- fp64 -- already cross the link; their narrowed images follow."""
         out = [None] * len(items)
         pending = []
-        if HOST_NARROW:
-            be = backend()
-            if be.name == "cuda":
-                from . import ingest
+        be = backend()
+        if HOST_NARROW not in ("0", False) and be.name == "cuda":
+            from . import ingest
+            if HOST_NARROW in ("1", True) or ingest.host_threads() >= HOST_NARROW_MIN_THREADS:
                 for i, (src, rep, width, shared) in enumerate(items):
                     if not isinstance(src, np.ndarray) or len(src) < HOST_NARROW_MIN_ROWS:
                         continue
