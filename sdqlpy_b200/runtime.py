@@ -179,9 +179,12 @@ STRIDE = os.environ.get("SDQLB200_STRIDE", "1") != "0"
 # (B200 box, 16 host cores, Q1 at SF100 end to end: 547 -> 430 ms per step, 28.8 -> 22.8 GB over the link; profiles/r02_visit16)
 # ... with 16 host threads for one rank.  Eight ranks on a 32-core box (4 threads each, the host's memory side already the
 # limit of the 8 concurrent uploads) lose with it: 100.8 -> 75.9 GB/s end to end (profiles/r02_visit14 / r02_visit18).
-# "auto" (default): narrow when the rank has at least HOST_NARROW_MIN_THREADS host threads to itself; "1" / "0": always / never
+# Four ranks with 8 threads each lose too: 115.1 -> 101.9 GB/s (profiles/r02_visit19) -- whenever several uploads share the
+# host's memory side, that side and not the link is the limit, and the narrowing pass adds traffic to it.
+# "auto" (default): narrow when the rank has at least HOST_NARROW_MIN_THREADS host threads to itself (one rank on a 16-core
+# box); "1" / "0": always / never
 HOST_NARROW = os.environ.get("SDQLB200_HOST_NARROW", "auto")
-HOST_NARROW_MIN_THREADS = int(os.environ.get("SDQLB200_HOST_NARROW_MIN_THREADS", "8"))
+HOST_NARROW_MIN_THREADS = int(os.environ.get("SDQLB200_HOST_NARROW_MIN_THREADS", "16"))
 HOST_NARROW_MIN_ROWS = int(os.environ.get("SDQLB200_HOST_NARROW_MIN_ROWS", str(1 << 20)))
 
 
