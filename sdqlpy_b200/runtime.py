@@ -299,7 +299,12 @@ def _encode(src, rep, width):
 
 class ColumnStore:
     """device copies keyed by (identity of the host column, representation) -- repeated calls with the same host
-    arrays (the reference's benchmark() loop, sdql_lib.py:445-452) do not re-upload."""
+    arrays (the reference's benchmark() loop, sdql_lib.py:445-452) do not re-upload.
+
+    Contract: a host array is treated as IMMUTABLE while its device copy is cached (the key is the buffer's address, size and
+    dtype; the reference re-reads the numpy buffer on every call and would see an in-place update, this store would not --
+    neither in the data nor in the min / max / dictionary derived from it).  After writing into an array in place call
+    ``STORE.invalidate(array)`` (or ``STORE.clear()``); ``STORE.enabled = False`` uploads on every call."""
 
     def __init__(self):
         self.cache = {}
@@ -413,6 +418,12 @@ class ColumnStore:
 
     def clear(self):
         self.cache.clear()
+
+    def invalidate(self, src):
+        """forget the device copies (every representation) of one host column: it was modified in place"""
+        k0 = self.key(src)
+        for k in [k for k in self.cache if k[0] == k0]:
+            del self.cache[k]
 
 
 _STORE = ColumnStore()

@@ -130,26 +130,41 @@ def parse_text(text, schema, want=None, delimiter="|", be=None, library=None, ro
     return n, host, dev
 
 
+def _no_blank_lines(buf):
+    """csv.reader -- the reference's read_csv, sdql_lib.py:79-82 -- yields [] for a blank line and the row loop adds nothing
+    for it: blank lines are skipped.  The device index counts every newline as a row end, so they are removed here (one
+    memmem over the block; dbgen output has none, so nothing is copied in the normal case)."""
+    if buf[:1] == b"\n" or b"\n\n" in buf:
+        import re
+        buf = re.sub(rb"\n\n+", b"\n", buf).lstrip(b"\n")
+    return buf
+
+
 def read_blocks(path, block_bytes):
-    """the file as blocks of whole rows (uint8 arrays), each at most ~block_bytes"""
+    """the file as blocks of whole rows (uint8 arrays), each at most ~block_bytes; blank lines removed"""
     size = os.path.getsize(path)
     with open(path, "rb") as f:
         carry = b""
         while True:
             buf = f.read(block_bytes)
             if not buf:
+                carry = _no_blank_lines(carry)
                 if carry:
                     yield np.frombuffer(carry, dtype=np.uint8)
                 return
             buf = carry + buf
             if f.tell() >= size:
-                yield np.frombuffer(buf, dtype=np.uint8)
+                buf = _no_blank_lines(buf)
+                if buf:
+                    yield np.frombuffer(buf, dtype=np.uint8)
                 return
             cut = buf.rfind(b"\n")
             if cut < 0:
                 carry = buf
                 continue
-            yield np.frombuffer(buf[:cut + 1], dtype=np.uint8)
+            head = _no_blank_lines(buf[:cut + 1])
+            if head:
+                yield np.frombuffer(head, dtype=np.uint8)
             carry = buf[cut + 1:]
 
 

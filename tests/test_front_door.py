@@ -223,3 +223,16 @@ def test_stride_statistic_is_verified_on_every_value():
     dense = g.columns("customer", ["c_custkey"])["c_custkey"].data
     assert runtime.stride_stat(dense, int(dense.min())) == 0
     assert runtime.stride_stat(ok[:100], int(ok.min())) == 0   # too few rows to bother
+
+
+def test_column_store_invalidate_forgets_one_host_column():
+    """ColumnStore contract: host arrays are immutable while cached; after an in-place update STORE.invalidate(array) drops
+    the device copies of exactly that column (every representation)"""
+    import numpy as np
+    st = runtime.ColumnStore()
+    a, b = np.arange(8, dtype=np.int64), np.arange(8, dtype=np.float64)
+    st.cache[(st.key(a), "i32", 0)] = ("dev_a", a)
+    st.cache[(st.key(a), "f64", 0)] = ("dev_a64", a)
+    st.cache[(st.key(b), "f64", 0)] = ("dev_b", b)
+    st.invalidate(a)
+    assert list(st.cache) == [(st.key(b), "f64", 0)]

@@ -201,3 +201,32 @@ def test_library_exports_declared_symbols():
     lib.sdqlb200_tbl_scratch_bytes.argtypes = [ctypes.c_int64]
     assert lib.sdqlb200_tbl_scratch_bytes(0) >= 256 and lib.sdqlb200_tbl_scratch_bytes(1 << 30) >= (1 << 30) // 4096 * 12
     assert ctypes.sizeof(tbl.TblStatus) == 8 * (2 + 2 * tbl.MAX_COLS) and ctypes.sizeof(tbl.TblCol) == 16
+
+
+def test_blank_lines_are_skipped_like_csv_reader_does(emu_tbl, tmp_path):
+    """csv.reader yields [] for a blank line and the reference's row loop adds nothing for it (sdql_lib.py:79-82): the same
+    columns with blank lines sprinkled over the text, in one block and in small blocks (a blank line at a block boundary)"""
+    import random
+    fx = json.load(open(FIXTURE))
+    table = "lineitem" if "lineitem" in fx["tables"] else sorted(fx["tables"])[0]
+    t = fx["tables"][table]
+    rows = t["text"].split("\n")
+    assert rows[-1] == ""
+    rnd = random.Random(5)
+    noisy = ["", ""]
+    for r in rows[:-1]:
+        noisy.append(r)
+        if rnd.random() < 0.3:
+            noisy += [""] * rnd.randint(1, 3)
+    path = os.path.join(tmp_path, "blank.tbl")
+    open(path, "w", newline="\n").write("\n".join(noisy) + "\n\n")
+    for block in (1 << 30, 700):
+        cols = tbl.parse_file(path, SCHEMAS[table], None, "|", block, emu_tbl[1], emu_tbl[0])
+        for name, kind in SCHEMAS[table]:
+            want, got = t["columns"][name], cols[name]
+            if isinstance(kind, tuple):
+                assert [str(x) for x in bytes_to_ustr(got.data, kind[1])] == want, name
+            elif kind == "float":
+                assert [float(x).hex() for x in got.data] == want, name
+            else:
+                assert [int(x) for x in got.data] == want, name
