@@ -5,7 +5,9 @@ The reference's generated module borrows the numpy buffers of ``db`` -- int64 fo
 string(n) -- by casting ``PyArray_DATA`` (sdql_compiler.py:644-668).  Here the raw buffer crosses PCIe once, in chunks
 through a staging buffer, and is narrowed (int64 -> int32 with min / max), cut to bytes (``<U n`` -> n bytes) or dictionary
 encoded (``<U n`` -> uint8 / int32 codes, every row checked against its dictionary entry) by HBM-speed kernels instead of
-numpy ``astype`` / ``np.unique`` passes on the host.  PyTorch provides device memory and the copies only."""
+numpy ``astype`` / ``np.unique`` passes on the host.  For a rank with enough host threads to itself, big int64 / ``<U1``
+columns are narrowed by host threads of the same library while the fp64 columns cross the link (``HostNarrow`` below,
+``runtime.ColumnStore.get_many``).  PyTorch provides device memory and the copies only."""
 import ctypes
 import os
 
@@ -155,8 +157,7 @@ def recode(col_holder, n, width, table, be):
     ranks agreed on); -> (pointer, holder, element bytes)"""
     t = be.torch
     src = col_holder[:n].to(t.int32)
-    w = 1 if int(table.max(initial=0)) < 256 and width == 1 else 4
-    w = 1 if len(table) and int(table.max()) < 256 else (4 if len(table) else width)
+    w = 1 if len(table) and int(table.max()) < 256 else (4 if len(table) else width)  # the merged dictionary's code width
     out = t.empty(max(n, 4), dtype=t.uint8 if w == 1 else t.int32, device=be.dev)
     tb = t.from_numpy(np.ascontiguousarray(table, dtype=np.int32)).to(be.dev)
     _ck(lib().sdqlb200_ingest_remap(src.data_ptr(), tb.data_ptr(), out.data_ptr(), w, n, be.stream()), "ingest_remap")
