@@ -489,6 +489,12 @@ class Kernel:
         if self.src[0] == "rel" and self.pipe_mode() == "tma":
             L += self.render_ring()
         elif self.src[0] == "rel":
+            # columns the evaluator touched but whose values no emitted line reads (payload fields of a build whose value is
+            # re-evaluated at the representative row later, vector elements that only count): not loaded at all
+            # (q21_k3 / q21_k4 streamed 2.4 GB of l_suppkey each for nothing)
+            text_ = "\n".join(self.pre + self.iter_pre + self.body + (self.body2 or []) + self.iter_post + self.post)
+            for key_ in [k_ for k_, (arr_, _) in self.scan_cols.items() if (arr_ + "[") not in text_]:
+                del self.scan_cols[key_]
             # software-pipelined streaming loop: the next group's column loads are issued before the current
             # group is processed, so every thread keeps two groups (2 x 4 rows x all columns) in flight
             ety = {"i32": "int", "f64": "double", "code": "int"}
